@@ -1,0 +1,117 @@
+"""ctypes binding of libmadgpu.so (C-ABI declared in include/madgpu.h).
+
+There is no fallback: if the shared library is missing or no B200 is visible the import / the
+first call raises.  Nothing in this package imports the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmadgpu.so")
+
+MADGPU_MAX_STEPS = 64
+
+SMOOTHER_GS, SMOOTHER_WJ = 0, 1
+CYCLE_V, CYCLE_FMG, CYCLE_SMOOTHER = 0, 1, 2
+PIX_U8, PIX_I16, PIX_F32, PIX_F64 = 0, 1, 2, 3
+
+K_NAMES = ["smooth0", "smoothc", "resid0", "restrict", "prolong", "coarse", "misc", "halo"]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("dim", C.c_int32),
+        ("size", C.c_int32 * 3),
+        ("spacing", C.c_double * 3),
+        ("time_step", C.c_double),
+        ("number_of_steps", C.c_int32),
+        ("cycle", C.c_int32),
+        ("iterations_per_grid", C.c_int32),
+        ("tolerance", C.c_double),
+        ("max_cycles", C.c_int32),
+        ("verbose", C.c_int32),
+        ("smoother", C.c_int32),
+        ("omega", C.c_double),
+        ("gs_colors", C.c_int32),
+        ("device", C.c_int32),
+        ("rank", C.c_int32),
+        ("world_size", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("steps", C.c_int32),
+        ("cycles_per_step", C.c_int32 * MADGPU_MAX_STEPS),
+        ("final_relres", C.c_double * MADGPU_MAX_STEPS),
+        ("total_cycles", C.c_int32),
+        ("levels", C.c_int32),
+        ("setup_ms", C.c_double),
+        ("h2d_ms", C.c_double),
+        ("d2h_ms", C.c_double),
+        ("solve_ms", C.c_double),
+        ("fmg_ms", C.c_double),
+        ("kernel_launches", C.c_int64),
+        ("prof_ms", C.c_double * 16),
+        ("prof_launches", C.c_int64 * 16),
+    ]
+
+
+EXPORTS = [
+    "madgpu_params_default", "madgpu_create", "madgpu_destroy", "madgpu_last_error", "madgpu_set_solver",
+    "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_set_tensor_device_f32", "madgpu_solve_cast",
+    "madgpu_solve_u8", "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_solve_device_f32",
+    "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info",
+    "madgpu_op_get_tensor", "madgpu_op_assemble", "madgpu_op_smooth", "madgpu_op_residual",
+    "madgpu_op_residual_f64", "madgpu_op_restrict", "madgpu_op_prolong", "madgpu_op_coarse_solve",
+    "madgpu_op_vcycle",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libmadgpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C multigridanisotropicdiffusion_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
+    L.madgpu_params_default.argtypes = [C.POINTER(Params)]
+    L.madgpu_params_default.restype = None
+    L.madgpu_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.madgpu_destroy.argtypes = [vp]
+    L.madgpu_destroy.restype = None
+    L.madgpu_last_error.argtypes = [vp]
+    L.madgpu_last_error.restype = C.c_char_p
+    L.madgpu_set_solver.argtypes = [vp, i32, f64, i32, i32, f64, i32, i32, i32]
+    L.madgpu_set_tensor_f32.argtypes = [vp, vp]
+    L.madgpu_set_tensor_f64.argtypes = [vp, vp]
+    L.madgpu_set_tensor_device_f32.argtypes = [vp, C.POINTER(vp)]
+    L.madgpu_solve_cast.argtypes = [vp, i32, vp, i32, vp, C.POINTER(Stats)]
+    for n in ("u8", "i16", "f32", "f64", "device_f32"):
+        getattr(L, "madgpu_solve_" + n).argtypes = [vp, vp, vp, C.POINTER(Stats)]
+    L.madgpu_get_relres_history.argtypes = [vp, C.POINTER(f64), i32]
+    L.madgpu_set_profiling.argtypes = [vp, i32]
+    L.madgpu_num_levels.argtypes = [vp]
+    L.madgpu_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]
+    L.madgpu_op_get_tensor.argtypes = [vp, i32, vp]
+    L.madgpu_op_assemble.argtypes = [vp, i32, vp]
+    L.madgpu_op_smooth.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    L.madgpu_op_residual.argtypes = [vp, i32, vp, vp, vp, C.POINTER(f64)]
+    L.madgpu_op_residual_f64.argtypes = [vp, vp, vp, vp, C.POINTER(f64)]
+    L.madgpu_op_restrict.argtypes = [vp, i32, vp, vp]
+    L.madgpu_op_prolong.argtypes = [vp, i32, vp, vp]
+    L.madgpu_op_coarse_solve.argtypes = [vp, vp, vp]
+    L.madgpu_op_vcycle.argtypes = [vp, i32, vp, vp, vp]
+    _lib = L
+    return L

@@ -1,0 +1,239 @@
+"""Host-side handle on one libmadgpu context (one GridsHierarchy + DirectSolver on one B200).
+
+`MadSolver` is the thin object the filter classes (filter.py) and the parity tests drive; every
+method is one C-ABI call (include/madgpu.h).  numpy arrays are (nz, ny, nx) / (ny, nx), x fastest,
+exactly the ITK buffer order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as B
+
+
+class MadGpuError(RuntimeError):
+    pass
+
+
+_PIX = {np.dtype(np.uint8): B.PIX_U8, np.dtype(np.int16): B.PIX_I16, np.dtype(np.float32): B.PIX_F32,
+        np.dtype(np.float64): B.PIX_F64}
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class MadSolver:
+    GS, WJ = B.SMOOTHER_GS, B.SMOOTHER_WJ
+    VCYCLE, FMG, SMOOTHER = B.CYCLE_V, B.CYCLE_FMG, B.CYCLE_SMOOTHER
+
+    def __init__(self, shape, spacing_xyz=None, time_step=0.01, smoother=B.SMOOTHER_GS, omega=2.0 / 3.0,
+                 iterations_per_grid=2, cycle=B.CYCLE_V, tolerance=1e-6, max_cycles=100, number_of_steps=1,
+                 verbose=False, gs_colors=4, device=0):
+        self._lib = B.load()
+        self._ctx = C.c_void_p()
+        self.shape = tuple(int(s) for s in shape)
+        self.dim = len(self.shape)
+        if self.dim not in (2, 3):
+            raise MadGpuError("images must be 2-D or 3-D")
+        p = B.Params()
+        self._lib.madgpu_params_default(C.byref(p))
+        p.dim = self.dim
+        size = list(self.shape[::-1]) + [1] * (3 - self.dim)
+        sp = list(spacing_xyz) if spacing_xyz is not None else [1.0] * self.dim
+        sp = sp + [1.0] * (3 - self.dim)
+        for d in range(3):
+            p.size[d] = size[d]
+            p.spacing[d] = float(sp[d])
+        p.time_step = float(time_step)
+        p.smoother = int(smoother)
+        p.omega = float(omega)
+        p.iterations_per_grid = int(iterations_per_grid)
+        p.cycle = int(cycle)
+        p.tolerance = float(tolerance)
+        p.max_cycles = int(max_cycles)
+        p.number_of_steps = int(number_of_steps)
+        p.verbose = int(bool(verbose))
+        p.gs_colors = int(gs_colors)
+        p.device = int(device)
+        self.params = p
+        rc = self._lib.madgpu_create(C.byref(p), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.madgpu_last_error(None)
+            self._ctx = C.c_void_p()
+            raise MadGpuError(f"madgpu_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.nlevels = self._lib.madgpu_num_levels(self._ctx)
+        self.levels = []
+        for l in range(self.nlevels):
+            n, h, c = (C.c_int32 * 3)(), (C.c_double * 3)(), (C.c_int32 * 3)()
+            self._lib.madgpu_level_info(self._ctx, l, n, h, c)
+            self.levels.append(dict(n=tuple(n)[: self.dim], h=tuple(h)[: self.dim], centering=tuple(c)[: self.dim],
+                                    shape=tuple(n)[: self.dim][::-1]))
+        self.ncomp = 3 if self.dim == 2 else 6
+        self.ns = 9 if self.dim == 2 else 27
+        self.last_stats = None
+
+    # ------------------------------------------------------------------ lifetime / errors
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.madgpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.madgpu_last_error(self._ctx)
+            raise MadGpuError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ------------------------------------------------------------------ configuration
+    def set_solver(self, smoother=None, omega=None, iterations_per_grid=None, cycle=None, tolerance=None,
+                   max_cycles=None, number_of_steps=None, verbose=None):
+        p = self.params
+        if smoother is not None: p.smoother = int(smoother)
+        if omega is not None: p.omega = float(omega)
+        if iterations_per_grid is not None: p.iterations_per_grid = int(iterations_per_grid)
+        if cycle is not None: p.cycle = int(cycle)
+        if tolerance is not None: p.tolerance = float(tolerance)
+        if max_cycles is not None: p.max_cycles = int(max_cycles)
+        if number_of_steps is not None: p.number_of_steps = int(number_of_steps)
+        if verbose is not None: p.verbose = int(bool(verbose))
+        self._check(self._lib.madgpu_set_solver(self._ctx, p.smoother, p.omega, p.iterations_per_grid, p.cycle,
+                                                p.tolerance, p.max_cycles, p.number_of_steps, p.verbose), "set_solver")
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.madgpu_set_profiling(self._ctx, int(on)), "set_profiling")
+
+    def set_tensor(self, tensor_aos: np.ndarray):
+        """ITK tensor buffer: shape image.shape + (ncomp,), float32 or float64."""
+        t = np.ascontiguousarray(tensor_aos)
+        if t.shape != self.shape + (self.ncomp,):
+            raise MadGpuError(f"tensor shape {t.shape} != {self.shape + (self.ncomp,)}")
+        if t.dtype == np.float32:
+            self._check(self._lib.madgpu_set_tensor_f32(self._ctx, _ptr(t)), "set_tensor_f32")
+        elif t.dtype == np.float64:
+            self._check(self._lib.madgpu_set_tensor_f64(self._ctx, _ptr(t)), "set_tensor_f64")
+        else:
+            raise MadGpuError("tensor dtype must be float32 or float64")
+
+    def set_tensor_device(self, plane_ptrs):
+        """ncomp device pointers (ints) to dense fp32 planes already resident in HBM."""
+        arr = (C.c_void_p * self.ncomp)(*[C.c_void_p(int(p)) for p in plane_ptrs])
+        self._check(self._lib.madgpu_set_tensor_device_f32(self._ctx, arr), "set_tensor_device_f32")
+
+    # ------------------------------------------------------------------ solve
+    def _stats(self, st: B.Stats):
+        d = dict(steps=st.steps, cycles_per_step=list(st.cycles_per_step)[: st.steps],
+                 final_relres=list(st.final_relres)[: st.steps], total_cycles=st.total_cycles, levels=st.levels,
+                 setup_ms=st.setup_ms, h2d_ms=st.h2d_ms, d2h_ms=st.d2h_ms, solve_ms=st.solve_ms, fmg_ms=st.fmg_ms,
+                 kernel_launches=st.kernel_launches,
+                 prof_ms={k: st.prof_ms[i] for i, k in enumerate(B.K_NAMES)},
+                 prof_launches={k: st.prof_launches[i] for i, k in enumerate(B.K_NAMES)})
+        self.last_stats = d
+        return d
+
+    def solve(self, image: np.ndarray, out_dtype=None) -> np.ndarray:
+        """GenerateData(): host image in, host image out (pixel type preserved unless out_dtype)."""
+        img = np.ascontiguousarray(image)
+        if img.shape != self.shape:
+            raise MadGpuError(f"image shape {img.shape} != {self.shape}")
+        if img.dtype not in _PIX:
+            raise MadGpuError(f"unsupported pixel type {img.dtype}")
+        odt = np.dtype(out_dtype) if out_dtype is not None else img.dtype
+        out = np.empty(self.shape, dtype=odt)
+        st = B.Stats()
+        st.struct_size = C.sizeof(B.Stats)
+        self._check(self._lib.madgpu_solve_cast(self._ctx, _PIX[img.dtype], _ptr(img), _PIX[odt], _ptr(out), C.byref(st)),
+                    "solve")
+        self._stats(st)
+        return out
+
+    def solve_device(self, d_in: int, d_out: int):
+        """Device-resident dense fp32 image in / out (raw device pointers)."""
+        st = B.Stats()
+        st.struct_size = C.sizeof(B.Stats)
+        self._check(self._lib.madgpu_solve_device_f32(self._ctx, C.c_void_p(int(d_in)), C.c_void_p(int(d_out)), C.byref(st)),
+                    "solve_device")
+        return self._stats(st)
+
+    def relres_history(self) -> np.ndarray:
+        p = self.params
+        h = np.full(p.number_of_steps * p.max_cycles, np.nan)
+        self._lib.madgpu_get_relres_history(self._ctx, h.ctypes.data_as(C.POINTER(C.c_double)), h.size)
+        return h.reshape(p.number_of_steps, p.max_cycles)
+
+    # ------------------------------------------------------------------ per-operator entry points (tests)
+    def _f32(self, a, level):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        if a.shape != self.levels[level]["shape"]:
+            raise MadGpuError(f"array shape {a.shape} != level {level} shape {self.levels[level]['shape']}")
+        return a
+
+    def op_get_tensor(self, level):
+        out = np.empty((self.ncomp,) + self.levels[level]["shape"], dtype=np.float32)
+        self._check(self._lib.madgpu_op_get_tensor(self._ctx, level, _ptr(out)), "op_get_tensor")
+        return out
+
+    def op_assemble(self, level):
+        out = np.empty(self.levels[level]["shape"] + (self.ns,), dtype=np.float32)
+        self._check(self._lib.madgpu_op_assemble(self._ctx, level, _ptr(out)), "op_assemble")
+        return out
+
+    def op_smooth(self, level, u, f, smoother=None, n_iter=1):
+        u, f = self._f32(u, level), self._f32(f, level)
+        out = np.empty_like(u)
+        sm = self.params.smoother if smoother is None else int(smoother)
+        self._check(self._lib.madgpu_op_smooth(self._ctx, level, sm, n_iter, _ptr(u), _ptr(f), _ptr(out)), "op_smooth")
+        return out
+
+    def op_residual(self, level, u, f):
+        u, f = self._f32(u, level), self._f32(f, level)
+        out = np.empty_like(u)
+        nrm = C.c_double()
+        self._check(self._lib.madgpu_op_residual(self._ctx, level, _ptr(u), _ptr(f), _ptr(out), C.byref(nrm)), "op_residual")
+        return out, nrm.value
+
+    def op_residual_f64(self, u, f):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        assert u.shape == self.shape and f.shape == self.shape
+        out = np.empty_like(u)
+        nrm = C.c_double()
+        self._check(self._lib.madgpu_op_residual_f64(self._ctx, _ptr(u), _ptr(f), _ptr(out), C.byref(nrm)), "op_residual_f64")
+        return out, nrm.value
+
+    def op_restrict(self, fine_level, fine):
+        fine = self._f32(fine, fine_level)
+        out = np.empty(self.levels[fine_level + 1]["shape"], dtype=np.float32)
+        self._check(self._lib.madgpu_op_restrict(self._ctx, fine_level, _ptr(fine), _ptr(out)), "op_restrict")
+        return out
+
+    def op_prolong(self, fine_level, coarse):
+        coarse = self._f32(coarse, fine_level + 1)
+        out = np.empty(self.levels[fine_level]["shape"], dtype=np.float32)
+        self._check(self._lib.madgpu_op_prolong(self._ctx, fine_level, _ptr(coarse), _ptr(out)), "op_prolong")
+        return out
+
+    def op_coarse_solve(self, f):
+        f = self._f32(f, self.nlevels - 1)
+        out = np.empty_like(f)
+        self._check(self._lib.madgpu_op_coarse_solve(self._ctx, _ptr(f), _ptr(out)), "op_coarse_solve")
+        return out
+
+    def op_vcycle(self, level, u, f):
+        u, f = self._f32(u, level), self._f32(f, level)
+        out = np.empty_like(u)
+        self._check(self._lib.madgpu_op_vcycle(self._ctx, level, _ptr(u), _ptr(f), _ptr(out)), "op_vcycle")
+        return out

@@ -1,0 +1,72 @@
+"""Shared helpers of the test-suite: seeded inputs handed identically to the oracle and the GPU path."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def random_spd_tensor(shape, seed=0, smooth=True, lo=0.05, hi=2.0):
+    """Random, smoothly varying SPD tensor field, AoS float32 (so oracle and GPU see identical values)."""
+    rng = np.random.default_rng(seed)
+    dim = len(shape)
+    ncomp = 3 if dim == 2 else 6
+    # random rotation field from smooth angles + random positive eigenvalues
+    def field():
+        f = rng.standard_normal(shape)
+        if smooth:
+            for ax in range(dim):
+                f = (np.roll(f, 1, ax) + 2 * f + np.roll(f, -1, ax)) / 4
+                f = (np.roll(f, 1, ax) + 2 * f + np.roll(f, -1, ax)) / 4
+        return f
+    if dim == 2:
+        th = 3.0 * field()
+        l1 = lo + (hi - lo) * (0.5 + 0.5 * np.tanh(2 * field()))
+        l2 = lo + (hi - lo) * (0.5 + 0.5 * np.tanh(2 * field()))
+        c, s = np.cos(th), np.sin(th)
+        T = np.empty(shape + (3,), dtype=np.float32)
+        T[..., 0] = l1 * c * c + l2 * s * s
+        T[..., 1] = (l1 - l2) * c * s
+        T[..., 2] = l1 * s * s + l2 * c * c
+        return T
+    A = np.stack([field() for _ in range(9)], axis=-1).reshape(shape + (3, 3))
+    Q, _ = np.linalg.qr(A)
+    lam = np.stack([lo + (hi - lo) * (0.5 + 0.5 * np.tanh(2 * field())) for _ in range(3)], axis=-1)
+    M = np.einsum("...ik,...k,...jk->...ij", Q, lam, Q)
+    T = np.empty(shape + (6,), dtype=np.float32)
+    T[..., 0] = M[..., 0, 0]; T[..., 1] = M[..., 0, 1]; T[..., 2] = M[..., 0, 2]
+    T[..., 3] = M[..., 1, 1]; T[..., 4] = M[..., 1, 2]; T[..., 5] = M[..., 2, 2]
+    assert T.shape[-1] == ncomp
+    return T
+
+
+def random_image(shape, seed=0, scale=100.0):
+    rng = np.random.default_rng(seed + 1000)
+    img = rng.standard_normal(shape)
+    for ax in range(len(shape)):
+        img = (np.roll(img, 1, ax) + 2 * img + np.roll(img, -1, ax)) / 4
+    return (scale * (1.0 + img)).astype(np.float32)
+
+
+def load_lena():
+    """512x512 uint8 decode of the reference's test/test_data/lena.jpg (fixture made by tests/golden/make_fixtures.py)."""
+    return np.load(os.path.join(GOLDEN, "lena_512_u8.npz"))["image"]
+
+
+def load_ved_test():
+    """69x77x69 int16 volume of the reference's test/test_data/ved_test.mhd/.zraw, spacing (.3125,.3125,.5)."""
+    z = np.load(os.path.join(GOLDEN, "ved_test_i16.npz"))
+    return z["image"], tuple(float(s) for s in z["spacing"])
