@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the multigrid anisotropic-diffusion hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+A "step" is ONE V(nu,nu) cycle of the 3-D VED diffusion step (GS smoother, nu=3, dt=0.1, the
+settings of the reference's test/itkVEDTest_GS.cxx) on a synthetic vessel volume, INCLUDING the
+level-0 residual-norm stop test and its read-back, exactly one pass of the reference's do-while body
+(itkMultigridAnisotropicDiffusionImageFilter.hxx:207-246).
+
+  value  : fine voxels / device time of one cycle, inputs resident in HBM (Mvoxel/s)
+  e2e    : the same metric through the filter call with HOST (pinned) buffers: one DiffusionStep
+           (SetDiffusionTensor + 4 time steps to tolerance 1e-10), tensor/image H2D and result D2H
+           inside the timed region; value = voxels x cycles executed / wall time
+  roofline: level-0 smoother sweep, 36 B/voxel algorithmic over the
+           CUDA-event time of those launches, against the measured HBM copy peak
+  cpu_baseline: the oracle restatement of the reference (lexicographic GS, double, 1 thread, with the
+           reference's redundant residual/norm passes) timed on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALG_BYTES_SWEEP_3D = 36.0  # u read + f read + u write + six tensor planes, fp32
+
+
+def alg_bytes_per_cycle(nu: int, dim: int = 3) -> float:
+    op = 24.0 if dim == 3 else 12.0
+    geo = 8.0 / 7.0 if dim == 3 else 4.0 / 3.0
+    return (2 * nu * (12 + op) + (8 + op + 0.5) + 8.5) * geo + (8 + op)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(size: int, nu: int, smoother: int, steps: int, warmup: int):
+    """The reference algorithm on the host: oracle V-cycles in `faithful` mode (the reference's redundant
+    residual + norm after every sweep, …Filter.hxx:384-411,437-439,460-487) plus the outer residual/norm."""
+    import numpy as np
+
+    from multigridanisotropicdiffusion_b200 import phantom
+    from oracle import oracle as O
+    shape = (size, size, size)
+    img_t, D = phantom.vessel_phantom(shape)
+    img = img_t.numpy().astype(np.float64)
+    T = phantom.planes_to_aos(D).numpy().astype(np.float64)
+    t0 = time.perf_counter()
+    o = O.Oracle(shape, phantom.VED_SPACING, T, 0.1, smoother=smoother, nu=nu)
+    setup_s = time.perf_counter() - t0
+    u = img.copy()
+    rhs_norm = O.l2norm(img)
+    relres = None
+    for _ in range(warmup):
+        u = o.vcycle(u, img, faithful=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u = o.vcycle(u, img, faithful=True)
+        relres = O.l2norm(o.residual(0, u, img)) / rhs_norm
+    dt = time.perf_counter() - t0
+    n = size ** 3
+    return dict(mvox_s=n * steps / dt / 1e6, s_per_cycle=dt / steps, setup_s=setup_s, relres=relres, voxels=n)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nu, sm = args.nu, (0 if args.smoother == "gs" else 1)
+    r = cpu_reference_run(args.cpu_size, nu, sm, args.steps, args.warmup)
+    line = {
+        "impl": "reference",
+        "metric": "3D VED V-cycle Mvoxels/s at 512^3", "value": r["mvox_s"], "unit": "Mvoxel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_cycle"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, "replicas" if args.gpus > 1 else "single"),
+        "cpu_baseline": {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.cpu_size}^3 sub-volume of the same phantom/tensor, {args.steps} V({nu},{nu}) cycles, "
+                                   "oracle restatement in faithful mode (reference cannot be built: ITK/VXL absent), setup "
+                                   f"{r['setup_s']:.1f}s excluded"},
+        "e2e": {"value": r["mvox_s"], "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, parallelism):
+    return {"workload": f"3-D VED diffusion step, synthetic {args.size}^3 float32 vessel phantom, spacing (.3125,.3125,.5), "
+                        f"analytic VED-form tensor (eps .01, omega 1.5), {args.smoother.upper()} smoother, V({args.nu},{args.nu}), dt 0.1",
+            "size": [args.size] * 3, "smoother": args.smoother, "iterations_per_grid": args.nu, "time_step": 0.1,
+            "parallelism": parallelism, "l2": "working set per sweep (>= 4.8 GB at 512^3) exceeds the 126 MB L2; no flush needed"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from multigridanisotropicdiffusion_b200 import MadSolver, phantom
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.size
+    shape = (n, n, n)
+    nvox = n ** 3
+    nu = args.nu
+    smoother = MadSolver.GS if args.smoother == "gs" else MadSolver.WJ
+    img, D = phantom.vessel_phantom(shape, device=dev)
+    torch.cuda.synchronize()
+
+    s = MadSolver(shape, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, tolerance=0.0,
+                  max_cycles=1 << 20, device=local_rank)
+    s.set_tensor_device([D[c].data_ptr() for c in range(6)])
+    s.cycles_begin(d_in=img.data_ptr())
+    # ---- device-resident timing: W warm-up cycles, then exactly K cycles ----
+    if args.warmup > 0:
+        s.cycles_run(args.warmup)
+    s.set_profiling(["smooth0"])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wall = time.perf_counter()
+    relres, dev_ms, st = s.cycles_run(args.steps)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop()
+    s.set_profiling(False)
+    ms_per_step = dev_ms / args.steps
+    if world > 1:
+        t = torch.tensor([ms_per_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())
+    # replicas: every rank runs its own volume (weak); a single volume is strong scaling
+    total_vox = nvox * world
+    value = total_vox / (ms_per_step * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: level-0 smoother sweeps ----
+    peak, peak_kind = measured_peaks()
+    sm_ms = st["prof_ms"]["smooth0"]
+    sm_launches = st["prof_launches"]["smooth0"]
+    sweeps = 2 * nu * args.steps
+    achieved = ALG_BYTES_SWEEP_3D * nvox * sweeps / (sm_ms * 1e-3) / 1e9 if sm_ms > 0 else None
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        ent = prof.get("smooth0", {})
+        if ent.get("size") == n and ent.get("smoother") == args.smoother:
+            traffic = ent.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "level-0 smoother sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "peak_kind": peak_kind, "traffic": traffic,
+                "alg_bytes_per_launch": ALG_BYTES_SWEEP_3D * nvox * sweeps / max(sm_launches, 1),
+                "launches": sm_launches, "ms_per_launch": sm_ms / max(sm_launches, 1),
+                "share_of_step": sm_ms / dev_ms if dev_ms > 0 else None,
+                "cycle_alg_bytes_per_voxel": alg_bytes_per_cycle(nu),
+                "cycle_frac": alg_bytes_per_cycle(nu) * nvox / (ms_per_step * 1e-3) / 1e9 / peak}
+    launches_timed = st["kernel_launches"]
+
+    # ---- e2e: the filter call with host (pinned) buffers ----
+    e2e = None
+    if args.e2e_reps > 0:
+        T_h = torch.empty(shape + (6,), dtype=torch.float32, pin_memory=True)
+        T_h.copy_(phantom.planes_to_aos(D))
+        img_h = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        img_h.copy_(img)
+        out_h = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        del D
+        torch.cuda.synchronize()
+        s.set_solver(tolerance=1e-10, max_cycles=100, number_of_steps=4)  # DiffusionStep of itkVEDTest_GS.cxx
+        T_np, img_np, out_np = T_h.numpy(), img_h.numpy(), out_h.numpy()
+        cycles = 0
+        times = []
+        for rep in range(args.e2e_reps + 1):  # first repetition is warm-up
+            barrier()
+            t0 = time.perf_counter()
+            s.set_tensor(T_np)
+            s.solve(img_np, out=out_np)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if rep > 0:
+                times.append(dt)
+                cycles = s.last_stats["total_cycles"]
+                launches_timed += s.last_stats["kernel_launches"]
+        dt = max(times)
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": total_vox * cycles / dt / 1e6, "unit": "Mvoxel/s",
+               "h2d_bytes_per_step": int(T_h.numel() * 4 + img_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
+               "call": "SetDiffusionTensor(host fp32 AoS) + solve(host fp32 image): 4 time steps to relres 1e-10",
+               "cycles_per_call": cycles, "s_per_call": dt, "cycles_per_step": s.last_stats["cycles_per_step"],
+               "final_relres": max(s.last_stats["final_relres"]), "setup_ms": s.last_stats["setup_ms"],
+               "h2d_ms": s.last_stats["h2d_ms"], "d2h_ms": s.last_stats["d2h_ms"]}
+    s.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.cpu_size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0)
+        cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": 1, "kind": "port",
+               "sample": f"{args.cpu_size}^3 sub-volume of the same phantom/tensor, {args.cpu_steps} V({nu},{nu}) cycles of the oracle "
+                         f"restatement in faithful mode (lexicographic GS, double, 1 thread; setup {r['setup_s']:.1f}s excluded)"}
+
+    if rank == 0:
+        line = {
+            "metric": "3D VED V-cycle Mvoxels/s at 512^3", "value": value, "unit": "Mvoxel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, "independent replicas (one volume per GPU)" if world > 1 else "single GPU"),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed), "clocks": clocks,
+            "relres_after_timed_cycles": float(relres[-1]) if len(relres) else None, "wall_ms_timed_region": wall_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--smoother", default="gs", choices=["gs", "wj"])
+    ap.add_argument("--nu", type=int, default=3)
+    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--e2e-reps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

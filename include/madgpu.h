@@ -145,9 +145,22 @@ int madgpu_solve_f64(madgpu_ctx *ctx, const double *in, double *out, madgpu_stat
 /* Same with DEVICE pointers to dense fp32 images (inputs already resident in HBM). */
 int madgpu_solve_device_f32(madgpu_ctx *ctx, const float *d_in, float *d_out, madgpu_stats *stats);
 
+/* Cycle-level driving of the same loop (benchmarks, per-V-cycle parity): begin stages the image and
+ * forms the first residual (…Filter.hxx:182-204), run executes exactly n outer iterations -- V-cycle
+ * (or smoother sweep in SMOOTHER mode) + fp64 residual + norm read-back, i.e. one pass of the do-while
+ * body (…Filter.hxx:207-246) each -- ignoring tolerance, and reports the device time of the n
+ * iterations measured with CUDA events on the library's stream; end casts the iterate out.
+ * relres (n doubles) and device_ms may be NULL. */
+int madgpu_cycles_begin_device_f32(madgpu_ctx *ctx, const float *d_in);
+int madgpu_cycles_begin_f32(madgpu_ctx *ctx, const float *in);
+int madgpu_cycles_run(madgpu_ctx *ctx, int32_t n, double *relres, float *device_ms, madgpu_stats *stats);
+int madgpu_cycles_end_device_f32(madgpu_ctx *ctx, float *d_out);
+int madgpu_cycles_end_f64(madgpu_ctx *ctx, double *out);
+
 /* relative residual after every cycle of the last solve: hist[step * max_cycles + cycle] */
 int madgpu_get_relres_history(const madgpu_ctx *ctx, double *hist, int32_t capacity);
 
+/* on: bit mask of kernel classes (1 << MADGPU_K_*) to time with CUDA events; 0 = off, -1 = all */
 int madgpu_set_profiling(madgpu_ctx *ctx, int32_t on);
 
 /* ---- hierarchy introspection (GridsHierarchy getters, mad/itkGridsHierarchy.h:86-113) ---- */

@@ -66,7 +66,8 @@ EXPORTS = [
     "madgpu_params_default", "madgpu_create", "madgpu_destroy", "madgpu_last_error", "madgpu_set_solver",
     "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_set_tensor_device_f32", "madgpu_solve_cast",
     "madgpu_solve_u8", "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_solve_device_f32",
-    "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info",
+    "madgpu_cycles_begin_device_f32", "madgpu_cycles_begin_f32", "madgpu_cycles_run",
+    "madgpu_cycles_end_device_f32", "madgpu_cycles_end_f64", "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info",
     "madgpu_op_get_tensor", "madgpu_op_assemble", "madgpu_op_smooth", "madgpu_op_residual",
     "madgpu_op_residual_f64", "madgpu_op_restrict", "madgpu_op_prolong", "madgpu_op_coarse_solve",
     "madgpu_op_vcycle",
@@ -100,6 +101,11 @@ def load() -> C.CDLL:
     L.madgpu_solve_cast.argtypes = [vp, i32, vp, i32, vp, C.POINTER(Stats)]
     for n in ("u8", "i16", "f32", "f64", "device_f32"):
         getattr(L, "madgpu_solve_" + n).argtypes = [vp, vp, vp, C.POINTER(Stats)]
+    L.madgpu_cycles_begin_device_f32.argtypes = [vp, vp]
+    L.madgpu_cycles_begin_f32.argtypes = [vp, vp]
+    L.madgpu_cycles_run.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(C.c_float), C.POINTER(Stats)]
+    L.madgpu_cycles_end_device_f32.argtypes = [vp, vp]
+    L.madgpu_cycles_end_f64.argtypes = [vp, vp]
     L.madgpu_get_relres_history.argtypes = [vp, C.POINTER(f64), i32]
     L.madgpu_set_profiling.argtypes = [vp, i32]
     L.madgpu_num_levels.argtypes = [vp]

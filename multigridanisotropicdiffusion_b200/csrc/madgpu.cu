@@ -69,7 +69,8 @@ struct madgpu_ctx {
   std::string err;
   std::vector<double> relres_hist;
   madgpu_stats st;
-  bool profiling;
+  int profiling;  // bit mask of kernel classes
+  double rhs_norm;  // of the current cycles_begin
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   int64_t launches;
@@ -128,7 +129,7 @@ struct Scope {
   madgpu_ctx* ctx;
   ProfEvent pe;
   bool on;
-  Scope(madgpu_ctx* c, int cls, int nlaunch = 1) : ctx(c), on(c->profiling)
+  Scope(madgpu_ctx* c, int cls, int nlaunch = 1) : ctx(c), on(((c->profiling >> cls) & 1) != 0)
   {
     ctx->launches += nlaunch;
     if (on) {
@@ -780,7 +781,7 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   ctx->ncomp = p->dim == 2 ? 3 : 6;
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
-  ctx->tensor_set = false; ctx->profiling = false; ctx->launches = 0;
+  ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
   ctx->u64 = ctx->f64 = nullptr;
   memset(&ctx->st, 0, sizeof ctx->st);
   auto bail = [&](int rc) { g_create_error = ctx->err; madgpu_destroy(ctx); return rc; };
@@ -954,6 +955,101 @@ int madgpu_solve_device_f32(madgpu_ctx* ctx, const float* d_in, float* d_out, ma
   return 0;
 }
 
+// ---- cycle-level driving --------------------------------------------------------------------
+static int cycles_begin_common(madgpu_ctx* ctx)
+{
+  Level& L = ctx->lv[0];
+  const size_t bytes64 = (size_t)L.g.plane * L.g.nz * sizeof(double);
+  const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
+  CU(cudaMemcpyAsync(ctx->u64, ctx->f64, bytes64, cudaMemcpyDeviceToDevice, ctx->stream));
+  k_sumsq<double><<<g, b, 0, ctx->stream>>>(L.g, ctx->f64, ctx->partials);
+  reduce_partials(ctx, (size_t)g.x * g.y * g.z);
+  ctx->rhs_norm = std::sqrt(read_scalar(ctx));
+  op_residual64(ctx, L.f, nullptr);
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int madgpu_cycles_begin_device_f32(madgpu_ctx* ctx, const float* d_in)
+{
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_in) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  CU(cudaSetDevice(ctx->p.device));
+  rc = stage_input(ctx, MADGPU_PIX_F32, d_in);
+  if (rc) return rc;
+  return cycles_begin_common(ctx);
+}
+
+int madgpu_cycles_begin_f32(madgpu_ctx* ctx, const float* in)
+{
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!in) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  CU(cudaSetDevice(ctx->p.device));
+  Level& L = ctx->lv[0];
+  const size_t nvox = (size_t)L.n[0] * L.n[1] * L.n[2];
+  float* stage = nullptr;
+  CU(cudaMalloc((void**)&stage, nvox * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(stage, in, nvox * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) { rc = stage_input(ctx, MADGPU_PIX_F32, stage); e = cudaStreamSynchronize(ctx->stream); }
+  cudaFree(stage);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, MADGPU_ECUDA, "input upload: %s", cudaGetErrorString(e));
+  return cycles_begin_common(ctx);
+}
+
+int madgpu_cycles_run(madgpu_ctx* ctx, int32_t n, double* relres, float* device_ms, madgpu_stats* stats)
+{
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (n < 0) return fail(ctx, MADGPU_EINVAL, "negative cycle count");
+  CU(cudaSetDevice(ctx->p.device));
+  begin_stats(ctx);
+  CU(cudaEventRecord(ctx->ev_a, ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    outer_iteration(ctx, ctx->p.cycle == MADGPU_CYCLE_SMOOTHER);
+    const double r = std::sqrt(read_scalar(ctx)) / ctx->rhs_norm;
+    if (relres) relres[i] = r;
+  }
+  CU(cudaEventRecord(ctx->ev_b, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev_b));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+  if (device_ms) *device_ms = ms;
+  ctx->st.solve_ms = ms;
+  ctx->st.total_cycles = n;
+  CU(cudaGetLastError());
+  end_stats(ctx, stats);
+  return 0;
+}
+
+int madgpu_cycles_end_device_f32(madgpu_ctx* ctx, float* d_out)
+{
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!d_out) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  CU(cudaSetDevice(ctx->p.device));
+  rc = stage_output(ctx, MADGPU_PIX_F32, d_out);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int madgpu_cycles_end_f64(madgpu_ctx* ctx, double* out)
+{
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!out) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  CU(cudaSetDevice(ctx->p.device));
+  Level& L = ctx->lv[0];
+  const size_t w = (size_t)L.g.nx * sizeof(double), dp = (size_t)L.g.pitch * sizeof(double), hrows = (size_t)L.g.ny * L.g.nz;
+  CU(cudaMemcpy2DAsync(out, w, ctx->u64, dp, w, hrows, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int madgpu_get_relres_history(const madgpu_ctx* ctx, double* hist, int32_t capacity)
 {
   if (!ctx || !hist) return MADGPU_EINVAL;
@@ -965,7 +1061,7 @@ int madgpu_get_relres_history(const madgpu_ctx* ctx, double* hist, int32_t capac
 int madgpu_set_profiling(madgpu_ctx* ctx, int32_t on)
 {
   if (!ctx) return MADGPU_EINVAL;
-  ctx->profiling = on != 0;
+  ctx->profiling = on;
   return 0;
 }
 

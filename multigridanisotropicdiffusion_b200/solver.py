@@ -114,7 +114,14 @@ class MadSolver:
                                                 p.tolerance, p.max_cycles, p.number_of_steps, p.verbose), "set_solver")
 
     def set_profiling(self, on=True):
-        self._check(self._lib.madgpu_set_profiling(self._ctx, int(on)), "set_profiling")
+        """on: True / False, or a list of kernel-class names (see _lib.K_NAMES) to time with CUDA events."""
+        if isinstance(on, (list, tuple)):
+            mask = 0
+            for k in on:
+                mask |= 1 << B.K_NAMES.index(k)
+        else:
+            mask = -1 if on else 0
+        self._check(self._lib.madgpu_set_profiling(self._ctx, mask), "set_profiling")
 
     def set_tensor(self, tensor_aos: np.ndarray):
         """ITK tensor buffer: shape image.shape + (ncomp,), float32 or float64."""
@@ -144,15 +151,19 @@ class MadSolver:
         self.last_stats = d
         return d
 
-    def solve(self, image: np.ndarray, out_dtype=None) -> np.ndarray:
-        """GenerateData(): host image in, host image out (pixel type preserved unless out_dtype)."""
+    def solve(self, image: np.ndarray, out_dtype=None, out: np.ndarray = None) -> np.ndarray:
+        """GenerateData(): host image in, host image out (pixel type preserved unless out_dtype).
+        `out` may be a preallocated (e.g. pinned) C-contiguous array of the output type."""
         img = np.ascontiguousarray(image)
         if img.shape != self.shape:
             raise MadGpuError(f"image shape {img.shape} != {self.shape}")
         if img.dtype not in _PIX:
             raise MadGpuError(f"unsupported pixel type {img.dtype}")
-        odt = np.dtype(out_dtype) if out_dtype is not None else img.dtype
-        out = np.empty(self.shape, dtype=odt)
+        odt = np.dtype(out_dtype) if out_dtype is not None else (out.dtype if out is not None else img.dtype)
+        if out is None:
+            out = np.empty(self.shape, dtype=odt)
+        elif out.shape != self.shape or out.dtype != odt or not out.flags.c_contiguous:
+            raise MadGpuError("out must be C-contiguous with the image shape and the output pixel type")
         st = B.Stats()
         st.struct_size = C.sizeof(B.Stats)
         self._check(self._lib.madgpu_solve_cast(self._ctx, _PIX[img.dtype], _ptr(img), _PIX[odt], _ptr(out), C.byref(st)),
@@ -167,6 +178,34 @@ class MadSolver:
         self._check(self._lib.madgpu_solve_device_f32(self._ctx, C.c_void_p(int(d_in)), C.c_void_p(int(d_out)), C.byref(st)),
                     "solve_device")
         return self._stats(st)
+
+    # cycle-level driving (benchmarks, per-V-cycle parity)
+    def cycles_begin(self, image=None, d_in=None):
+        if d_in is not None:
+            self._check(self._lib.madgpu_cycles_begin_device_f32(self._ctx, C.c_void_p(int(d_in))), "cycles_begin_device")
+        else:
+            img = np.ascontiguousarray(image, dtype=np.float32)
+            if img.shape != self.shape:
+                raise MadGpuError(f"image shape {img.shape} != {self.shape}")
+            self._check(self._lib.madgpu_cycles_begin_f32(self._ctx, _ptr(img)), "cycles_begin")
+
+    def cycles_run(self, n):
+        """n outer iterations; returns (relres[n], device_ms, stats)."""
+        rr = np.empty(max(n, 1), dtype=np.float64)
+        ms = C.c_float()
+        st = B.Stats()
+        st.struct_size = C.sizeof(B.Stats)
+        self._check(self._lib.madgpu_cycles_run(self._ctx, int(n), rr.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ms),
+                                                C.byref(st)), "cycles_run")
+        return rr[:n], float(ms.value), self._stats(st)
+
+    def cycles_end(self, d_out=None):
+        if d_out is not None:
+            self._check(self._lib.madgpu_cycles_end_device_f32(self._ctx, C.c_void_p(int(d_out))), "cycles_end_device")
+            return None
+        out = np.empty(self.shape, dtype=np.float64)
+        self._check(self._lib.madgpu_cycles_end_f64(self._ctx, _ptr(out)), "cycles_end")
+        return out
 
     def relres_history(self) -> np.ndarray:
         p = self.params

@@ -136,9 +136,12 @@ class Oracle:
                                     shape=tuple(nn)[: self.dim][::-1]))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().mo_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().mo_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def set_smoother(self, smoother, omega=2.0 / 3.0, nu=2):
         lib().mo_set_smoother(self._h, int(smoother), float(omega), int(nu))
