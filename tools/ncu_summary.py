@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs into the text files kept under profiles/.
+
+  python tools/ncu_summary.py launches <launches.csv>     # per-kernel totals and shares of a launch list
+  python tools/ncu_summary.py full <report.ncu-rep>       # key metrics per captured launch (needs ncu on PATH)
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
+        "smsp__cycles_active.avg", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[h]
+    kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[h + 1:]:
+        if len(r) <= mv:
+            continue
+        v = float(r[mv].replace(",", ""))
+        u = r[mu]
+        v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v * 1e6 if u == "s" else v
+        name = r[kn].split("(")[0]
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"# {path}: {sum(v[0] for v in agg.values())} launches, {tot / 1e3:.3f} ms total (ncu serialised, cold cache)")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[1]:12.1f} us {100 * v[1] / tot:5.1f}%  n={v[0]:5d}  avg {v[1] / v[0]:10.1f} us  {k}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    print(f"# {path}")
+    for r in rows[2:]:
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print(f"{w:90s} {r[i]} {units[i]}")
+        try:
+            rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
+            wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd *= scale[units[hdr.index("dram__bytes_read.sum")]]
+            wr *= scale[units[hdr.index("dram__bytes_write.sum")]]
+            t = float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))
+            t *= {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1}[units[hdr.index("gpu__time_duration.sum")]]
+            print(f"{'-> dram traffic (read+write) per launch':90s} {rd + wr:.0f} byte; {(rd + wr) / t / 1e9:.1f} GB/s")
+        except Exception as e:  # noqa
+            print("   (traffic not computed:", e, ")")
+        print()
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
