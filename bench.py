@@ -199,7 +199,7 @@ def run_ours(args):
     # ---- device-resident timing: W warm-up cycles, then exactly K cycles ----
     if args.warmup > 0:
         s.cycles_run(args.warmup)
-    s.set_profiling(["smooth0"])
+    s.set_profiling(True)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -237,6 +237,8 @@ def run_ours(args):
                 "alg_bytes_per_launch": ALG_BYTES_SWEEP_3D * nvox * sweeps / max(sm_launches, 1),
                 "launches": sm_launches, "ms_per_launch": sm_ms / max(sm_launches, 1),
                 "share_of_step": sm_ms / dev_ms if dev_ms > 0 else None,
+                "class_ms_per_cycle": {k: v / args.steps for k, v in st["prof_ms"].items() if v > 0},
+                "class_launches_per_cycle": {k: v / args.steps for k, v in st["prof_launches"].items() if v > 0},
                 "cycle_alg_bytes_per_voxel": alg_bytes_per_cycle(nu),
                 "cycle_frac": alg_bytes_per_cycle(nu) * nvox / (ms_per_step * 1e-3) / 1e9 / peak}
     launches_timed = st["kernel_launches"]

@@ -15,6 +15,7 @@
 // residual doubles as the stop test of the previous cycle, so it costs one pass, not two.
 #include "../../include/madgpu.h"
 #include "mad_kernels.cuh"
+#include "mad_fast.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -74,6 +75,8 @@ struct madgpu_ctx {
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   int64_t launches;
+  int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
+  int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
 };
 
 namespace {
@@ -111,6 +114,47 @@ int dalloc(madgpu_ctx* ctx, std::vector<void*>& owner, T** out, size_t n)
 
 dim3 block3(int dim) { return dim == 3 ? dim3(32, 4, 4) : dim3(32, 16, 1); }
 dim3 grid3(const Geom& g, dim3 b) { return dim3((g.nx + b.x - 1) / b.x, (g.ny + b.y - 1) / b.y, (g.nz + b.z - 1) / b.z); }
+
+Tensor tensor_of(const Level& L);
+
+// ---- streaming (mad_fast.cuh) launch geometry -------------------------------------------------
+bool use_fast(const madgpu_ctx* ctx, const Level& L) { return ctx->dim == 3 && L.g.nx >= ctx->fast_min_nx && L.g.nz >= 3 && L.g.ny >= 3; }
+// planes per CTA: enough CTAs for ~8 waves of the resident set, at least 8 planes so that the two start-up planes stay cheap
+int fast_zc(const Geom& g, int wy)
+{
+  const long long cxy = (long long)((g.nx + fast::TX - 1) / fast::TX) * ((g.ny + wy - 1) / wy);
+  const long long want = 148ll * 3 * 8;
+  long long chunks = std::max(1ll, want / std::max(1ll, cxy));
+  int zc = (int)std::max(8ll, (g.nz + chunks - 1) / chunks);
+  return std::min(zc, std::max(g.nz, 1));
+}
+dim3 fast_grid(const Geom& g, int wy, int zc) { return dim3((g.nx + fast::TX - 1) / fast::TX, (g.ny + wy - 1) / wy, (g.nz + zc - 1) / zc); }
+
+// One streaming pass (MODE_WJ / MODE_RES) over a level; returns the number of CTAs (= partial sums written).
+// ctx->fast_cfg selects the CTA shape / register cap (tuning hook MADGPU_FAST_CFG).
+template <int MODE, typename T, typename UT, typename FT, typename OT>
+size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT* out, double* partials, float omega)
+{
+  const Tensor D = tensor_of(L);
+#define MAD_FAST_LAUNCH(WY, MINB)                                                                                            \
+  do {                                                                                                                       \
+    const int zc = fast_zc(L.g, WY);                                                                                         \
+    const dim3 fg = fast_grid(L.g, WY, zc);                                                                                  \
+    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc); \
+    return (size_t)fg.x * fg.y * fg.z;                                                                                       \
+  } while (0)
+  if (sizeof(T) == 8) {
+    if (ctx->fast_cfg == 1) MAD_FAST_LAUNCH(8, 1);
+    MAD_FAST_LAUNCH(4, 2);
+  }
+  switch (ctx->fast_cfg) {
+    case 1: MAD_FAST_LAUNCH(8, 1);
+    case 2: MAD_FAST_LAUNCH(8, 2);
+    case 3: MAD_FAST_LAUNCH(4, 4);
+    default: MAD_FAST_LAUNCH(4, 3);
+  }
+#undef MAD_FAST_LAUNCH
+}
 
 // ---- launch bookkeeping -------------------------------------------------------------------
 cudaEvent_t get_event(madgpu_ctx* ctx)
@@ -186,7 +230,8 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
   for (int it = 0; it < n_iter; ++it) {
     if (smoother == MADGPU_SMOOTHER_WJ) {
       Scope s(ctx, cls);
-      if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
+      if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega);
+      else if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       else k_jacobi<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       std::swap(L.u, L.tmp);
     } else {
@@ -221,6 +266,11 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
   Scope s(ctx, MADGPU_K_RESTRICT, norm ? 2 : 1);
   const Tensor D = tensor_of(L);
   double* part = norm ? ctx->partials : nullptr;
+  if (use_fast(ctx, L)) {
+    const size_t nb = launch_fast<fast::MODE_RES, float, float, float, float>(ctx, L, L.u, L.f, out, part, 0.f);
+    if (norm) reduce_partials(ctx, nb);
+    return;
+  }
   if (ctx->dim == 3) k_residual<3, float, float, float, float><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, out, part);
   else k_residual<2, float, float, float, float><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, out, part);
   if (norm) reduce_partials(ctx, (size_t)g.x * g.y * g.z);
@@ -236,6 +286,10 @@ void op_residual64(madgpu_ctx* ctx, float* r32_or_null, double* r64_or_null)
   if (r64_or_null) {
     if (ctx->dim == 3) k_residual<3, double, double, double, double><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
     else k_residual<2, double, double, double, double><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
+  } else if (use_fast(ctx, L)) {
+    const size_t nb = launch_fast<fast::MODE_RES, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f);
+    reduce_partials(ctx, nb);
+    return;
   } else {
     if (ctx->dim == 3) k_residual<3, double, double, double, float><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
     else k_residual<2, double, double, double, float><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
@@ -512,7 +566,7 @@ int build_coarse_solver(madgpu_ctx* ctx)
 {
   Level& L = ctx->lv[ctx->nlevels - 1];
   const long long nv = (long long)L.n[0] * L.n[1] * L.n[2];
-  if (nv > 4096) {
+  if (nv > 2048) {  // dense inverse costs O(n^3) on the host; larger coarsest grids (thin volumes) are iterated instead
     ctx->coarse_direct = false;
     ctx->ncoarse = 0;
     return 0;
@@ -782,6 +836,12 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
   ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
+  {
+    const char* e = getenv("MADGPU_FAST_MIN_NX");  // test hook: 0 forces the streaming kernels on every 3-D level
+    ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
+    e = getenv("MADGPU_FAST_CFG");
+    ctx->fast_cfg = e ? atoi(e) : 0;
+  }
   ctx->u64 = ctx->f64 = nullptr;
   memset(&ctx->st, 0, sizeof ctx->st);
   auto bail = [&](int rc) { g_create_error = ctx->err; madgpu_destroy(ctx); return rc; };
@@ -1153,6 +1213,13 @@ int madgpu_op_residual_f64(madgpu_ctx* ctx, const double* u, const double* f, do
   const size_t w = (size_t)L.g.nx * sizeof(double), dp = (size_t)L.g.pitch * sizeof(double), hrows = (size_t)L.g.ny * L.g.nz;
   CU(cudaMemcpy2DAsync(ctx->u64, dp, u, w, w, hrows, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpy2DAsync(ctx->f64, dp, f, w, w, hrows, cudaMemcpyHostToDevice, ctx->stream));
+  if (!r) {  // norm only: the kernel of the solve loop (fp32 residual into lv[0].tmp + fp64 norm)
+    op_residual64(ctx, L.tmp, nullptr);
+    if (norm) *norm = std::sqrt(read_scalar(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    return 0;
+  }
   double* d_r = nullptr;
   CU(cudaMalloc((void**)&d_r, L.elems * sizeof(double)));
   op_residual64(ctx, nullptr, d_r + L.g.plane);

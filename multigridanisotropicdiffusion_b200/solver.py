@@ -244,13 +244,15 @@ class MadSolver:
         self._check(self._lib.madgpu_op_residual(self._ctx, level, _ptr(u), _ptr(f), _ptr(out), C.byref(nrm)), "op_residual")
         return out, nrm.value
 
-    def op_residual_f64(self, u, f):
+    def op_residual_f64(self, u, f, norm_only=False):
+        """norm_only: run the kernel of the solve loop (fp32 residual kept on the device, fp64 norm returned)."""
         u = np.ascontiguousarray(u, dtype=np.float64)
         f = np.ascontiguousarray(f, dtype=np.float64)
         assert u.shape == self.shape and f.shape == self.shape
-        out = np.empty_like(u)
+        out = None if norm_only else np.empty_like(u)
         nrm = C.c_double()
-        self._check(self._lib.madgpu_op_residual_f64(self._ctx, _ptr(u), _ptr(f), _ptr(out), C.byref(nrm)), "op_residual_f64")
+        self._check(self._lib.madgpu_op_residual_f64(self._ctx, _ptr(u), _ptr(f), _ptr(out) if out is not None else None,
+                                                     C.byref(nrm)), "op_residual_f64")
         return out, nrm.value
 
     def op_restrict(self, fine_level, fine):
