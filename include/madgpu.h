@@ -168,6 +168,13 @@ int madgpu_num_levels(const madgpu_ctx *ctx);
 /* size / spacing / centering (0 vertex, 1 cell: how level l was obtained from l-1) of level l */
 int madgpu_level_info(const madgpu_ctx *ctx, int32_t level, int32_t size[3], double spacing[3], int32_t centering[3]);
 
+/* Ordering of the Gauss-Seidel sweep on a level (the reference sweeps lexicographically,
+ * mad/itkMultigridGaussSeidelSmoother.h:87-100).  tile = {0,0,0}: multicolour, one pass per colour over
+ * the whole level.  Otherwise the fused sweep: the level is cut in tiles of tile[0] x tile[1] x tile[2]
+ * voxels (x, y, z); inside a tile planes are relaxed in z order, each plane as even rows (even x, odd x)
+ * then odd rows; values outside the tile are those of the previous sweep. */
+int madgpu_gs_tile(const madgpu_ctx *ctx, int32_t level, int32_t tile[3]);
+
 /* ---- per-operator entry points (isolated parity tests; HOST dense fp32 buffers of the level's size) ---- */
 /* restricted tensor planes of a level: ncomp * nvox floats, SoA (mad/itkGridsHierarchy.hxx:149-162) */
 int madgpu_op_get_tensor(madgpu_ctx *ctx, int32_t level, float *planes);

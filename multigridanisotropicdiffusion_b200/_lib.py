@@ -67,7 +67,7 @@ EXPORTS = [
     "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_set_tensor_device_f32", "madgpu_solve_cast",
     "madgpu_solve_u8", "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_solve_device_f32",
     "madgpu_cycles_begin_device_f32", "madgpu_cycles_begin_f32", "madgpu_cycles_run",
-    "madgpu_cycles_end_device_f32", "madgpu_cycles_end_f64", "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info",
+    "madgpu_cycles_end_device_f32", "madgpu_cycles_end_f64", "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info", "madgpu_gs_tile",
     "madgpu_op_get_tensor", "madgpu_op_assemble", "madgpu_op_smooth", "madgpu_op_residual",
     "madgpu_op_residual_f64", "madgpu_op_restrict", "madgpu_op_prolong", "madgpu_op_coarse_solve",
     "madgpu_op_vcycle",
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     L.madgpu_cycles_end_f64.argtypes = [vp, vp]
     L.madgpu_get_relres_history.argtypes = [vp, C.POINTER(f64), i32]
     L.madgpu_set_profiling.argtypes = [vp, i32]
+    L.madgpu_gs_tile.argtypes = [vp, i32, C.POINTER(i32)]
     L.madgpu_num_levels.argtypes = [vp]
     L.madgpu_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]
     L.madgpu_op_get_tensor.argtypes = [vp, i32, vp]

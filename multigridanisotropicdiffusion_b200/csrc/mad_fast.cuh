@@ -4,7 +4,12 @@
 // z-differentiated tensor components (xz, yz, zz) held in REGISTERS.  x-neighbours come from warp
 // shuffles (plus one scalar load at the two warp ends), y-neighbour rows are re-loaded through L1
 // (the neighbouring warp of the same CTA loads the same lines at the same time), so every field is
-// fetched from HBM once per sweep: 36 B/voxel (u, f, u', six tensor planes).
+// fetched from HBM once per sweep: 36 B/voxel (u, f, u', six tensor planes) -- ncu: 36.05 B/voxel.
+//
+// Latency is hidden by software pipelining, not by occupancy (the marching state costs ~170
+// registers): a plane step first consumes the raw registers loaded during the previous step,
+// immediately ISSUES every load of the next step (~11 KB per warp in flight, nothing in between
+// depends on a loaded value) and only then does the arithmetic.
 //
 // The operator row is evaluated on the fly in the closed form of row_coeffs()/apply_offdiag()
 // (mad_kernels.cuh; reference: mad/itkGridsHierarchy.hxx:298-516) with node-mirrored reads at the
@@ -13,9 +18,6 @@
 //   k_fast_sweep<MODE_WJ>   mad/itkMultigridWeightedJacobiSmoother.hxx:33-102
 //   k_fast_sweep<MODE_RES>  mad/itkMultigridGaussSeidelSmoother.hxx:114-180 (+ L2Norm partial sums,
 //                           itkMultigridAnisotropicDiffusionImageFilter.hxx:496-515)
-//   k_fast_gs               mad/itkMultigridGaussSeidelSmoother.hxx:33-111 in the ordering
-//                           "planes in z order; inside a plane even rows (even x, then odd x), then
-//                           odd rows", exact inside a CTA tile, previous-sweep values outside it.
 #pragma once
 #include "mad_kernels.cuh"
 
@@ -34,11 +36,17 @@ struct V6 {
   T v[6];  // v[0] = x-1, v[1..4] = the thread's four voxels, v[5] = x+4
 };
 
-// Per-thread position inside the volume.
+// Per-thread position inside the volume.  All element offsets are 32-bit (the host only selects
+// these kernels for levels with fewer than 2^31 elements per field).
 struct Pos {
-  int xt, lane, y, jl, hx;
-  bool act, edge, ylo, yhi;
-  long long oym, oyp;  // element offsets of the mirrored y-1 / y+1 rows relative to row y
+  int xt;    // x of the thread's first voxel
+  int xl;    // x the thread loads from: xt, or 0 in lanes right of the image (their results are discarded)
+  int lane, y, jl;
+  int dh;    // halo voxel fetched by the warp-end lanes, relative to xl: x-1 in lane 0, x+4 in lane 31
+  bool edge; // lane 0 or 31
+  bool xb;   // this thread holds x = 0 or x = nx-1
+  bool ylo, yhi;
+  int oym, oyp;  // element offsets of the mirrored y-1 / y+1 rows relative to row y
 };
 
 __device__ __forceinline__ Pos make_pos(const Geom& g)
@@ -47,20 +55,20 @@ __device__ __forceinline__ Pos make_pos(const Geom& g)
   p.lane = threadIdx.x;
   p.xt = blockIdx.x * TX + p.lane * 4;
   p.y = blockIdx.y * blockDim.y + threadIdx.y;
-  p.act = p.xt < g.nx;
+  p.xl = p.xt < g.nx ? p.xt : 0;
   p.jl = g.nx - 1 - p.xt;
   p.edge = p.lane == 0 || p.lane == 31;
-  p.hx = p.lane == 0 ? max(p.xt - 1, 0) : min(p.xt + 4, g.nx - 1);  // x of the halo voxel the warp-end lanes fetch
+  p.dh = (p.lane == 0 ? max(p.xt - 1, 0) : min(p.xt + 4, g.nx - 1)) - p.xl;
+  p.xb = p.xt == 0 || (p.jl >= 0 && p.jl < 4);
   p.ylo = p.y == 0;
   p.yhi = p.y == g.ny - 1;
-  p.oym = p.ylo ? g.pitch : -(long long)g.pitch;
-  p.oyp = p.yhi ? -(long long)g.pitch : g.pitch;
+  p.oym = p.ylo ? g.pitch : -g.pitch;
+  p.oyp = p.yhi ? -g.pitch : g.pitch;
   return p;
 }
 
-// Loads are split in two phases so that a plane step first ISSUES every load it needs (nothing in
-// between depends on a loaded value, the warp keeps ~11 KB in flight) and only then consumes them:
-// issue4/issue6 return the raw registers, finish4/finish6 convert and exchange the x-neighbours.
+// ---- two-phase loads: issue4/issue6 return the raw registers, finish4/finish6 convert and exchange
+// ---- the x-neighbours.  `o` is the element offset of the thread's first voxel.
 template <typename ST>
 struct Raw4;
 template <>
@@ -77,30 +85,26 @@ struct Raw6 {
   ST h;  // halo voxel, meaningful in lanes 0 (x-1) and 31 (x+4)
 };
 
-__device__ __forceinline__ Raw4<float> issue4(const float* __restrict__ row, const Pos& p)
+__device__ __forceinline__ Raw4<float> issue4(const float* __restrict__ base, int o)
 {
   Raw4<float> r;
-  r.q = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.act) r.q = __ldg(reinterpret_cast<const float4*>(row + p.xt));
+  r.q = __ldg(reinterpret_cast<const float4*>(base + o));
   return r;
 }
-__device__ __forceinline__ Raw4<double> issue4(const double* __restrict__ row, const Pos& p)
+__device__ __forceinline__ Raw4<double> issue4(const double* __restrict__ base, int o)
 {
   Raw4<double> r;
-  r.a = r.b = make_double2(0.0, 0.0);
-  if (p.act) {
-    r.a = __ldg(reinterpret_cast<const double2*>(row + p.xt));
-    r.b = __ldg(reinterpret_cast<const double2*>(row + p.xt + 2));
-  }
+  r.a = __ldg(reinterpret_cast<const double2*>(base + o));
+  r.b = __ldg(reinterpret_cast<const double2*>(base + o) + 1);
   return r;
 }
 template <typename ST>
-__device__ __forceinline__ Raw6<ST> issue6(const ST* __restrict__ row, const Pos& p)
+__device__ __forceinline__ Raw6<ST> issue6(const ST* __restrict__ base, int o, const Pos& p)
 {
   Raw6<ST> r;
-  r.c = issue4(row, p);
+  r.c = issue4(base, o);
   r.h = ST(0);
-  if (p.edge) r.h = __ldg(row + p.hx);
+  if (p.edge) r.h = __ldg(base + o + p.dh);
   return r;
 }
 
@@ -132,18 +136,6 @@ __device__ __forceinline__ V6<T> finish6(const Raw6<ST>& r, const Pos& p)
   return w;
 }
 
-// one-shot forms (start-up planes, boundary rows)
-template <typename T, typename ST>
-__device__ __forceinline__ V4<T> load4(const ST* __restrict__ row, const Pos& p)
-{
-  return finish4<T>(issue4(row, p));
-}
-template <typename T, typename ST>
-__device__ __forceinline__ V6<T> load6(const ST* __restrict__ row, const Pos& p)
-{
-  return finish6<T, ST>(issue6(row, p), p);
-}
-
 // Node mirror along x for fields the stencil is applied to: u(-1) = u(1), u(nx) = u(nx-2).
 // jl = nx-1-xt is the slot of the last voxel of the row when it lies in this thread.
 template <typename T>
@@ -155,17 +147,18 @@ __device__ __forceinline__ void mirror_x(V6<T>& w, int xt, int jl)
     if (jl == j) w.v[j + 2] = w.v[j];
 }
 
-// x-difference of a tensor component at slot j (mad/itkGridsHierarchy.hxx:451-470)
+// One-sided x-difference of a tensor component for the slot that lies on the x boundary
+// (mad/itkGridsHierarchy.hxx:451-470); only called by threads with p.xb.
 template <typename T>
-__device__ __forceinline__ T xdiff(const V6<float>& w, int j, int xt, int jl, const float* __restrict__ row)
+__device__ __forceinline__ void xdiff_boundary(const V6<float>& w, const Pos& p, const float* __restrict__ base, int o, T d[4])
 {
-  T d = T(w.v[j + 2]) - T(w.v[j]);
-  if (xt == 0 && j == 0) d = T(-3) * T(w.v[1]) + T(4) * T(w.v[2]) - T(w.v[3]);
-  if (jl == j) {
-    const T m2 = j >= 1 ? T(w.v[j - 1]) : T(__ldg(row + xt - 2));
-    d = T(3) * T(w.v[j + 1]) - T(4) * T(w.v[j]) + m2;
-  }
-  return d;
+  if (p.xt == 0) d[0] = T(-3) * T(w.v[1]) + T(4) * T(w.v[2]) - T(w.v[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (p.jl == j) {
+      const T m2 = j >= 1 ? T(w.v[j - 1]) : T(__ldg(base + o - 2));
+      d[j] = T(3) * T(w.v[j + 1]) - T(4) * T(w.v[j]) + m2;
+    }
 }
 
 // The tensor is kept in registers as stored (fp32); differences are formed in the arithmetic type T.
@@ -206,20 +199,23 @@ __device__ __forceinline__ V4<T> mid4(const V6<T>& w)
 }
 
 template <typename OT>
-__device__ __forceinline__ void store4(OT* __restrict__ row, int xt, int nx, const float v[4])
+__device__ __forceinline__ void store4(OT* __restrict__ base, int o, int xt, int nx, const float v[4])
 {
   if (xt + 3 < nx) {
-    if constexpr (sizeof(OT) == 4) *reinterpret_cast<float4*>(row + xt) = make_float4(v[0], v[1], v[2], v[3]);
+    if constexpr (sizeof(OT) == 4) *reinterpret_cast<float4*>(base + o) = make_float4(v[0], v[1], v[2], v[3]);
     else {
-      *reinterpret_cast<double2*>(row + xt) = make_double2(v[0], v[1]);
-      *reinterpret_cast<double2*>(row + xt + 2) = make_double2(v[2], v[3]);
+      *reinterpret_cast<double2*>(base + o) = make_double2(v[0], v[1]);
+      *(reinterpret_cast<double2*>(base + o) + 1) = make_double2(v[2], v[3]);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (xt + j < nx) row[xt + j] = OT(v[j]);
+      if (xt + j < nx) base[o + j] = OT(v[j]);
   }
 }
+
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 
 // Tensor rows of one plane step: everything the row of A needs besides u.
 template <typename T>
@@ -240,12 +236,12 @@ struct DzRaw {
   Raw6<float> xz;
   Raw4<float> yz, zz;
 };
-__device__ __forceinline__ DzRaw issue_dz(const Tensor& D, long long rowoff, const Pos& p)
+__device__ __forceinline__ DzRaw issue_dz(const Tensor& D, int o, const Pos& p)
 {
   DzRaw r;
-  r.xz = issue6(D.p[XZ3] + rowoff, p);
-  r.yz = issue4(D.p[YZ3] + rowoff, p);
-  r.zz = issue4(D.p[ZZ3] + rowoff, p);
+  r.xz = issue6(D.p[XZ3], o, p);
+  r.yz = issue4(D.p[YZ3], o);
+  r.zz = issue4(D.p[ZZ3], o);
   return r;
 }
 
@@ -254,67 +250,84 @@ struct DcRaw {
   Raw6<float> xx, xy;
   Raw4<float> xy_m, xy_p, yy, yy_m, yy_p, yz_ym, yz_yp;
 };
-__device__ __forceinline__ DcRaw issue_dc(const Tensor& D, long long rowoff, const Pos& p)
+__device__ __forceinline__ DcRaw issue_dc(const Tensor& D, int o, const Pos& p)
 {
   DcRaw r;
-  r.xx = issue6(D.p[XX3] + rowoff, p);
-  r.xy = issue6(D.p[XY3] + rowoff, p);
-  r.xy_m = issue4(D.p[XY3] + rowoff + p.oym, p);
-  r.xy_p = issue4(D.p[XY3] + rowoff + p.oyp, p);
-  r.yy = issue4(D.p[YY3] + rowoff, p);
-  r.yy_m = issue4(D.p[YY3] + rowoff + p.oym, p);
-  r.yy_p = issue4(D.p[YY3] + rowoff + p.oyp, p);
-  r.yz_ym = issue4(D.p[YZ3] + rowoff + p.oym, p);
-  r.yz_yp = issue4(D.p[YZ3] + rowoff + p.oyp, p);
+  const int om = o + p.oym, op = o + p.oyp;
+  r.xx = issue6(D.p[XX3], o, p);
+  r.xy = issue6(D.p[XY3], o, p);
+  r.xy_m = issue4(D.p[XY3], om);
+  r.xy_p = issue4(D.p[XY3], op);
+  r.yy = issue4(D.p[YY3], o);
+  r.yy_m = issue4(D.p[YY3], om);
+  r.yy_p = issue4(D.p[YY3], op);
+  r.yz_ym = issue4(D.p[YZ3], om);
+  r.yz_yp = issue4(D.p[YZ3], op);
   return r;
 }
+struct DcFin {
+  V6<float> xx, xy;
+  V4<float> xy_m, xy_p, yy, yy_m, yy_p, yz_ym, yz_yp;
+};
+__device__ __forceinline__ DcFin finish_dc(const DcRaw& R, const Pos& p)
+{
+  DcFin F;
+  F.xx = finish6<float, float>(R.xx, p); F.xy = finish6<float, float>(R.xy, p);
+  F.xy_m = finish4<float>(R.xy_m); F.xy_p = finish4<float>(R.xy_p);
+  F.yy = finish4<float>(R.yy); F.yy_m = finish4<float>(R.yy_m); F.yy_p = finish4<float>(R.yy_p);
+  F.yz_ym = finish4<float>(R.yz_ym); F.yz_yp = finish4<float>(R.yz_yp);
+  return F;
+}
 
-// Coefficients of the four rows of A at plane z (rowoff = element offset of row (y, z)).
+// Coefficients of the four rows of A at plane z (o = element offset of the thread's first voxel).
 template <typename T>
-__device__ __forceinline__ void coefficients(const Geom& g, const Tensor& D, const Pos& p, int z, long long rowoff, const DzState& S,
-                                             const DcRaw& R, Coef<T>& c)
+__device__ __forceinline__ void coefficients(const Geom& g, const Tensor& D, const Pos& p, int z, int o, const DzState& S, const DcFin& F,
+                                             Coef<T>& c)
 {
   const GeomConst<T> k(g);
-  typedef V4<float> F4;
-  typedef V6<float> F6;
-  const F6 xx = finish6<float, float>(R.xx, p), xy = finish6<float, float>(R.xy, p);
-  const F4 xy_m = finish4<float>(R.xy_m), xy_p = finish4<float>(R.xy_p);
-  const F4 yy = finish4<float>(R.yy), yy_m = finish4<float>(R.yy_m), yy_p = finish4<float>(R.yy_p);
-  const F4 yz_ym = finish4<float>(R.yz_ym), yz_yp = finish4<float>(R.yz_yp);
-
   // y-differences (central; one-sided on the first / last row -- warp-uniform branches)
-  V4<T> dy_xy = sub4<T>(xy_p, xy_m), dy_yy = sub4<T>(yy_p, yy_m), dy_yz = sub4<T>(yz_yp, yz_ym);
+  V4<T> dy_xy = sub4<T>(F.xy_p, F.xy_m), dy_yy = sub4<T>(F.yy_p, F.yy_m), dy_yz = sub4<T>(F.yz_yp, F.yz_ym);
   if (p.ylo || p.yhi) {
-    const long long o2 = p.ylo ? 2ll * g.pitch : -2ll * g.pitch;
+    const int o2 = o + (p.ylo ? 2 * g.pitch : -2 * g.pitch);
     const T sgn = p.ylo ? T(-1) : T(1);
-    dy_xy = onesided4<T>(mid4(xy), sel4(p.ylo, xy_p, xy_m), load4<float, float>(D.p[XY3] + rowoff + o2, p), sgn);
-    dy_yy = onesided4<T>(yy, sel4(p.ylo, yy_p, yy_m), load4<float, float>(D.p[YY3] + rowoff + o2, p), sgn);
-    dy_yz = onesided4<T>(S.yz_c, sel4(p.ylo, yz_yp, yz_ym), load4<float, float>(D.p[YZ3] + rowoff + o2, p), sgn);
+    dy_xy = onesided4<T>(mid4(F.xy), sel4(p.ylo, F.xy_p, F.xy_m), finish4<float>(issue4(D.p[XY3], o2)), sgn);
+    dy_yy = onesided4<T>(F.yy, sel4(p.ylo, F.yy_p, F.yy_m), finish4<float>(issue4(D.p[YY3], o2)), sgn);
+    dy_yz = onesided4<T>(S.yz_c, sel4(p.ylo, F.yz_yp, F.yz_ym), finish4<float>(issue4(D.p[YZ3], o2)), sgn);
   }
   // z-differences
   V4<T> dz_xz = sub4<T>(mid4(S.xz_p), S.xz_m), dz_yz = sub4<T>(S.yz_p, S.yz_m), dz_zz = sub4<T>(S.zz_p, S.zz_m);
   const bool zlo = z == 0 && g.zlo_phys, zhi = z == g.nz - 1 && g.zhi_phys;
   if (zlo || zhi) {
-    const long long o2 = zlo ? 2 * g.plane : -2 * g.plane;
+    const int o2 = o + (int)(zlo ? 2 * g.plane : -2 * g.plane);
     const T sgn = zlo ? T(-1) : T(1);
-    dz_xz = onesided4<T>(mid4(S.xz_c), sel4(zlo, mid4(S.xz_p), S.xz_m), load4<float, float>(D.p[XZ3] + rowoff + o2, p), sgn);
-    dz_yz = onesided4<T>(S.yz_c, sel4(zlo, S.yz_p, S.yz_m), load4<float, float>(D.p[YZ3] + rowoff + o2, p), sgn);
-    dz_zz = onesided4<T>(S.zz_c, sel4(zlo, S.zz_p, S.zz_m), load4<float, float>(D.p[ZZ3] + rowoff + o2, p), sgn);
+    dz_xz = onesided4<T>(mid4(S.xz_c), sel4(zlo, mid4(S.xz_p), S.xz_m), finish4<float>(issue4(D.p[XZ3], o2)), sgn);
+    dz_yz = onesided4<T>(S.yz_c, sel4(zlo, S.yz_p, S.yz_m), finish4<float>(issue4(D.p[YZ3], o2)), sgn);
+    dz_zz = onesided4<T>(S.zz_c, sel4(zlo, S.zz_p, S.zz_m), finish4<float>(issue4(D.p[ZZ3], o2)), sgn);
+  }
+  // x-differences (central; the slot on the x boundary is redone one-sided by the few threads that hold it)
+  T dx_xx[4], dx_xy[4], dx_xz[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    dx_xx[j] = T(F.xx.v[j + 2]) - T(F.xx.v[j]);
+    dx_xy[j] = T(F.xy.v[j + 2]) - T(F.xy.v[j]);
+    dx_xz[j] = T(S.xz_c.v[j + 2]) - T(S.xz_c.v[j]);
+  }
+  if (p.xb) {
+    xdiff_boundary<T>(F.xx, p, D.p[XX3], o, dx_xx);
+    xdiff_boundary<T>(F.xy, p, D.p[XY3], o, dx_xy);
+    xdiff_boundary<T>(S.xz_c, p, D.p[XZ3], o, dx_xz);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const T ax = k.wx * T(xx.v[j + 1]), ay = k.wy * T(yy.v[j]), az = k.wz * T(S.zz_c.v[j]);
+    const T ax = k.wx * T(F.xx.v[j + 1]), ay = k.wy * T(F.yy.v[j]), az = k.wz * T(S.zz_c.v[j]);
     c.diag[j] = T(1) + T(2) * (ax + ay + az);
-    const T dx_xx = xdiff<T>(xx, j, p.xt, p.jl, D.p[XX3] + rowoff);
-    const T dx_xy = xdiff<T>(xy, j, p.xt, p.jl, D.p[XY3] + rowoff);
-    const T dx_xz = xdiff<T>(S.xz_c, j, p.xt, p.jl, D.p[XZ3] + rowoff);
-    const T bx = -(k.bxx * dx_xx + k.bxy * dy_xy.v[j] + k.bxz * dz_xz.v[j]);
-    const T by = -(k.bxy * dx_xy + k.byy * dy_yy.v[j] + k.byz * dz_yz.v[j]);
-    const T bz = -(k.bxz * dx_xz + k.byz * dy_yz.v[j] + k.bzz * dz_zz.v[j]);
+    const T bx = -(k.bxx * dx_xx[j] + k.bxy * dy_xy.v[j] + k.bxz * dz_xz.v[j]);
+    const T by = -(k.bxy * dx_xy[j] + k.byy * dy_yy.v[j] + k.byz * dz_yz.v[j]);
+    const T bz = -(k.bxz * dx_xz[j] + k.byz * dy_yz.v[j] + k.bzz * dz_zz.v[j]);
     c.xp[j] = -ax + bx; c.xm[j] = -ax - bx;
     c.yp[j] = -ay + by; c.ym[j] = -ay - by;
     c.zp[j] = -az + bz; c.zm[j] = -az - bz;
-    c.exy[j] = -k.cxy * T(xy.v[j + 1]);
+    c.exy[j] = -k.cxy * T(F.xy.v[j + 1]);
     c.exz[j] = -k.cxz * T(S.xz_c.v[j + 1]);
     c.eyz[j] = -k.cyz * T(S.yz_c.v[j]);
   }
@@ -330,21 +343,22 @@ struct URaw {
   Raw6<UT> r[3];
 };
 template <typename UT>
-__device__ __forceinline__ URaw<UT> issue_u(const UT* __restrict__ u, long long rowoff, const Pos& p)
+__device__ __forceinline__ URaw<UT> issue_u(const UT* __restrict__ u, int o, const Pos& p)
 {
   URaw<UT> R;
-  R.r[0] = issue6(u + rowoff + p.oym, p);
-  R.r[1] = issue6(u + rowoff, p);
-  R.r[2] = issue6(u + rowoff + p.oyp, p);
+  R.r[0] = issue6(u, o + p.oym, p);
+  R.r[1] = issue6(u, o, p);
+  R.r[2] = issue6(u, o + p.oyp, p);
   return R;
 }
 template <typename T, typename UT>
 __device__ __forceinline__ void finish_u(const URaw<UT>& R, const Pos& p, UPlane<T>& P)
 {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    P.r[i] = finish6<T, UT>(R.r[i], p);
-    mirror_x(P.r[i], p.xt, p.jl);
+  for (int i = 0; i < 3; ++i) P.r[i] = finish6<T, UT>(R.r[i], p);
+  if (p.xb) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) mirror_x(P.r[i], p.xt, p.jl);
   }
 }
 
@@ -360,16 +374,38 @@ __device__ __forceinline__ T offdiag(const Coef<T>& c, const UPlane<T>& m, const
   return s;
 }
 
-__device__ __forceinline__ long long zmirror_lo(const Geom& g, int z) { return (z == 0 && g.zlo_phys) ? 1 : z - 1; }
-__device__ __forceinline__ long long zmirror_hi(const Geom& g, int z) { return (z == g.nz - 1 && g.zhi_phys) ? g.nz - 2 : z + 1; }
+__device__ __forceinline__ int zmirror_lo(const Geom& g, int z) { return (z == 0 && g.zlo_phys) ? 1 : z - 1; }
+__device__ __forceinline__ int zmirror_hi(const Geom& g, int z) { return (z == g.nz - 1 && g.zhi_phys) ? g.nz - 2 : z + 1; }
+
+// every load of one plane step: u and the z-marched tensor rows of plane z+1, the plane-z-only tensor rows, f
+template <typename UT, typename FT>
+struct StepRaw {
+  URaw<UT> u;
+  DzRaw dz;
+  DcRaw dc;
+  Raw4<FT> f;
+};
+template <typename UT, typename FT>
+__device__ __forceinline__ StepRaw<UT, FT> issue_step(const Geom& g, const Tensor& D, const UT* __restrict__ u, const FT* __restrict__ f,
+                                                      const Pos& p, int rowo, int z)
+{
+  StepRaw<UT, FT> R;
+  const int oc = z * (int)g.plane + rowo, on = zmirror_hi(g, z) * (int)g.plane + rowo;
+  R.u = issue_u(u, on, p);
+  R.dz = issue_dz(D, on, p);
+  R.dc = issue_dc(D, oc, p);
+  R.f = issue4(f, oc);
+  return R;
+}
 
 enum { MODE_WJ = 0, MODE_RES = 1 };
 
 // One pass over the volume.  MODE_WJ: out = weighted-Jacobi update of u.  MODE_RES: out = f - A u
 // (out may be null) and per-CTA partial sums of its squares (partials may be null).
 // grid = (ceil(nx/128), ceil(ny/WY), ceil(nz/zc)), block = (32, WY); MINB = CTAs per SM the register
-// allocation is capped for.
-template <int MODE, typename T, typename UT, typename FT, typename OT, int WY, int MINB>
+// allocation is capped for; PF = issue the loads of step z+1 before the arithmetic of step z (needs ~70 more
+// registers) instead of at the top of step z+1.
+template <int MODE, typename T, typename UT, typename FT, typename OT, int WY, int MINB, bool PF>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, const UT* __restrict__ u, const FT* __restrict__ f,
                                                          OT* __restrict__ out, double* __restrict__ partials, float omega, int zc)
 {
@@ -378,31 +414,34 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
   double sq = 0.0;
   if (valid) {
     const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
-    const long long rowy = (long long)p.y * g.pitch;
+    const int rowo = p.y * g.pitch + p.xl;
+    const T om = T(omega), om1 = T(1) - T(omega);
     UPlane<T> um, uc, up;
     DzState S;
     {
-      const long long om = zmirror_lo(g, z0) * g.plane + rowy, oc = (long long)z0 * g.plane + rowy;
-      const URaw<UT> r0 = issue_u(u, om, p), r1 = issue_u(u, oc, p);
-      const DzRaw d0 = issue_dz(D, om, p), d1 = issue_dz(D, oc, p);
+      const int o_m = zmirror_lo(g, z0) * (int)g.plane + rowo, o_c = z0 * (int)g.plane + rowo;
+      const URaw<UT> r0 = issue_u(u, o_m, p), r1 = issue_u(u, o_c, p);
+      const DzRaw d0 = issue_dz(D, o_m, p), d1 = issue_dz(D, o_c, p);
       finish_u<T, UT>(r0, p, um);
       finish_u<T, UT>(r1, p, uc);
       S.xz_m = finish4<float>(d0.xz.c); S.yz_m = finish4<float>(d0.yz); S.zz_m = finish4<float>(d0.zz);
       S.xz_c = finish6<float, float>(d1.xz, p); S.yz_c = finish4<float>(d1.yz); S.zz_c = finish4<float>(d1.zz);
     }
+    StepRaw<UT, FT> R;
+    if (PF) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z0);
+#pragma unroll 2
     for (int z = z0; z < z1; ++z) {
-      const long long oc = (long long)z * g.plane + rowy, on = zmirror_hi(g, z) * g.plane + rowy;
-      // ---- issue every load of this plane step ----
-      const URaw<UT> ru = issue_u(u, on, p);
-      const DzRaw rd = issue_dz(D, on, p);
-      const DcRaw rc = issue_dc(D, oc, p);
-      const Raw4<FT> rf = issue4(f + oc, p);
-      // ---- consume ----
-      finish_u<T, UT>(ru, p, up);
-      S.xz_p = finish6<float, float>(rd.xz, p); S.yz_p = finish4<float>(rd.yz); S.zz_p = finish4<float>(rd.zz);
-      const V4<T> fv = finish4<T>(rf);
+      const int oc = z * (int)g.plane + rowo;
+      if (!PF) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z);
+      // ---- consume the loads issued one step ago ----
+      finish_u<T, UT>(R.u, p, up);
+      S.xz_p = finish6<float, float>(R.dz.xz, p); S.yz_p = finish4<float>(R.dz.yz); S.zz_p = finish4<float>(R.dz.zz);
+      const DcFin F = finish_dc(R.dc, p);
+      const V4<T> fv = finish4<T>(R.f);
+      // ---- issue every load of the next plane step before doing any arithmetic ----
+      if (PF && z + 1 < z1) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z + 1);
       Coef<T> c;
-      coefficients<T>(g, D, p, z, oc, S, rc, c);
+      coefficients<T>(g, D, p, z, oc, S, F, c);
       float res[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -410,14 +449,14 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
         const T uj = uc.r[1].v[j + 1];
         if (MODE == MODE_WJ) {
           // mad/itkMultigridWeightedJacobiSmoother.hxx:88-89
-          res[j] = float((fv.v[j] - s) * (T(omega) / c.diag[j]) + (T(1) - T(omega)) * uj);
+          res[j] = float((fv.v[j] - s) * fast_div(om, c.diag[j]) + om1 * uj);
         } else {
           const T r = fv.v[j] - c.diag[j] * uj - s;
           res[j] = float(r);
           if (p.xt + j < g.nx) sq += (double)r * (double)r;
         }
       }
-      if (out && p.act) store4<OT>(out + oc, p.xt, g.nx, res);
+      if (out && p.xt < g.nx) store4<OT>(out, oc, p.xt, g.nx, res);
       um = uc; uc = up;
       S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
       S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
@@ -427,6 +466,113 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
     const double t = block_sum(sq);
     if (threadIdx.x == 0 && threadIdx.y == 0)
       partials[(size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)] = t;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Gauss-Seidel sweep (mad/itkMultigridGaussSeidelSmoother.hxx:33-111) in ONE pass over the volume.
+// Ordering: planes in z order (as the reference's outer loop); inside a plane the even rows first
+// (even x, then odd x), then the odd rows -- the four in-plane colours of the 9-point plane stencil,
+// so no two voxels updated together are coupled and every update sees the newest value of every
+// neighbour that precedes it: a true Gauss-Seidel ordering INSIDE a CTA tile (128 x WY x zc voxels).
+// Values outside the tile are read from the previous sweep (`u`; the result goes to `out`), i.e. tile
+// faces are relaxed Jacobi-style.  All orderings share the fixed point A u = f, which is what the
+// parity bound for Gauss-Seidel is stated on; tools/gs_order_experiment.py shows the V-cycle
+// convergence factor of this ordering next to the reference's lexicographic one.
+//
+// New values travel: own row -> registers; x-neighbours -> warp shuffles; rows y+-1 of the plane
+// being updated and of the plane below -> shared memory (two row buffers, alternating with z).
+// ------------------------------------------------------------------------------------------
+template <int WY, int MINB>
+__global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, const float* __restrict__ u, const float* __restrict__ f,
+                                                             float* __restrict__ out, int zc)
+{
+  static_assert(WY % 2 == 0, "row colours alternate with the warp index");
+  __shared__ float4 sh[2][WY][32];
+  const Pos p = make_pos(g);
+  const int w = threadIdx.y;
+  const bool valid = p.y < g.ny;
+  const int wm = p.ylo ? w + 1 : w - 1, wp = p.yhi ? w - 1 : w + 1;  // tile rows holding the (mirrored) y-1 / y+1 rows
+  const bool has_m = wm >= 0 && wm < WY, has_p = wp >= 0 && wp < WY && blockIdx.y * WY + wp < g.ny;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
+  const int rowo = (valid ? p.y : 0) * g.pitch + p.xl;
+  UPlane<float> um, uc, up;
+  DzState S;
+  {
+    const int o_m = zmirror_lo(g, z0) * (int)g.plane + rowo, o_c = z0 * (int)g.plane + rowo;
+    const URaw<float> r0 = issue_u(u, o_m, p), r1 = issue_u(u, o_c, p);
+    const DzRaw d0 = issue_dz(D, o_m, p), d1 = issue_dz(D, o_c, p);
+    finish_u<float, float>(r0, p, um);
+    finish_u<float, float>(r1, p, uc);
+    S.xz_m = finish4<float>(d0.xz.c); S.yz_m = finish4<float>(d0.yz); S.zz_m = finish4<float>(d0.zz);
+    S.xz_c = finish6<float, float>(d1.xz, p); S.yz_c = finish4<float>(d1.yz); S.zz_c = finish4<float>(d1.zz);
+  }
+  for (int z = z0; z < z1; ++z) {
+    const int oc = z * (int)g.plane + rowo;
+    const int cb = z & 1, pb = cb ^ 1;
+    const StepRaw<float, float> R = issue_step<float, float>(g, D, u, f, p, rowo, z);
+    finish_u<float, float>(R.u, p, up);
+    S.xz_p = finish6<float, float>(R.dz.xz, p); S.yz_p = finish4<float>(R.dz.yz); S.zz_p = finish4<float>(R.dz.zz);
+    const DcFin F = finish_dc(R.dc, p);
+    const V4<float> fv = finish4<float>(R.f);
+    Coef<float> c;
+    coefficients<float>(g, D, p, z, oc, S, F, c);
+    // plane z-1 was updated one step ago: rows y+-1 come from the tile's row buffer (own row: registers)
+    if (z > z0) {
+      if (has_m) { const float4 q = sh[pb][wm][p.lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
+      if (has_p) { const float4 q = sh[pb][wp][p.lane]; um.r[2].v[1] = q.x; um.r[2].v[2] = q.y; um.r[2].v[3] = q.z; um.r[2].v[4] = q.w; }
+    }
+    // last plane of the image: the mirrored plane z+1 IS plane z-1, which has already been updated
+    if (z == g.nz - 1 && g.zhi_phys) up = um;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+      if (valid && (w & 1) == phase) {
+        if (phase == 1) {
+          // odd row: rows y+-1 of this plane are even rows, updated in phase 0
+          const float* sm = reinterpret_cast<const float*>(&sh[cb][has_m ? wm : 0][0]);
+          const float* sp = reinterpret_cast<const float*>(&sh[cb][has_p ? wp : 0][0]);
+          if (has_m) {
+            const float4 q = reinterpret_cast<const float4*>(sm)[p.lane];
+            uc.r[0].v[1] = q.x; uc.r[0].v[2] = q.y; uc.r[0].v[3] = q.z; uc.r[0].v[4] = q.w;
+            if (p.lane > 0) uc.r[0].v[0] = sm[p.lane * 4 - 1];
+            if (p.lane < 31) uc.r[0].v[5] = sm[p.lane * 4 + 4];
+          }
+          if (has_p) {
+            const float4 q = reinterpret_cast<const float4*>(sp)[p.lane];
+            uc.r[2].v[1] = q.x; uc.r[2].v[2] = q.y; uc.r[2].v[3] = q.z; uc.r[2].v[4] = q.w;
+            if (p.lane > 0) uc.r[2].v[0] = sp[p.lane * 4 - 1];
+            if (p.lane < 31) uc.r[2].v[5] = sp[p.lane * 4 + 4];
+          }
+          if (p.xb) { mirror_x(uc.r[0], p.xt, p.jl); mirror_x(uc.r[2], p.xt, p.jl); }
+        }
+        // even x (slots 0, 2): x-neighbours still hold the values of the previous sweep
+        const float n0 = fast_div(fv.v[0] - offdiag<float>(c, um, uc, up, 0), c.diag[0]);  // mad/itkMultigridGaussSeidelSmoother.hxx:99
+        const float n2 = fast_div(fv.v[2] - offdiag<float>(c, um, uc, up, 2), c.diag[2]);
+        uc.r[1].v[1] = n0; uc.r[1].v[3] = n2;
+        {
+          const float r = __shfl_down_sync(FULL, n0, 1);
+          if (p.lane < 31) uc.r[1].v[5] = r;
+          if (p.xb) mirror_x(uc.r[1], p.xt, p.jl);
+        }
+        // odd x (slots 1, 3)
+        const float n1 = fast_div(fv.v[1] - offdiag<float>(c, um, uc, up, 1), c.diag[1]);
+        const float n3 = fast_div(fv.v[3] - offdiag<float>(c, um, uc, up, 3), c.diag[3]);
+        uc.r[1].v[2] = n1; uc.r[1].v[4] = n3;
+        {
+          const float l = __shfl_up_sync(FULL, n3, 1);
+          if (p.lane > 0) uc.r[1].v[0] = l;
+          if (p.xb) mirror_x(uc.r[1], p.xt, p.jl);
+        }
+        sh[cb][w][p.lane] = make_float4(n0, n1, n2, n3);
+        const float res[4] = {n0, n1, n2, n3};
+        if (p.xt < g.nx) store4<float>(out, oc, p.xt, g.nx, res);
+      }
+      __syncthreads();
+    }
+    um = uc; uc = up;
+    S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
+    S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
   }
 }
 

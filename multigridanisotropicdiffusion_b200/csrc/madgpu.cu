@@ -75,6 +75,7 @@ struct madgpu_ctx {
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   int64_t launches;
+  int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
 };
@@ -118,7 +119,10 @@ dim3 grid3(const Geom& g, dim3 b) { return dim3((g.nx + b.x - 1) / b.x, (g.ny + 
 Tensor tensor_of(const Level& L);
 
 // ---- streaming (mad_fast.cuh) launch geometry -------------------------------------------------
-bool use_fast(const madgpu_ctx* ctx, const Level& L) { return ctx->dim == 3 && L.g.nx >= ctx->fast_min_nx && L.g.nz >= 3 && L.g.ny >= 3; }
+bool use_fast(const madgpu_ctx* ctx, const Level& L)
+{
+  return ctx->dim == 3 && L.g.nx >= ctx->fast_min_nx && L.g.nz >= 3 && L.g.ny >= 3 && L.elems < (1ull << 31);  // 32-bit element offsets
+}
 // planes per CTA: enough CTAs for ~8 waves of the resident set, at least 8 planes so that the two start-up planes stay cheap
 int fast_zc(const Geom& g, int wy)
 {
@@ -136,22 +140,22 @@ template <int MODE, typename T, typename UT, typename FT, typename OT>
 size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT* out, double* partials, float omega)
 {
   const Tensor D = tensor_of(L);
-#define MAD_FAST_LAUNCH(WY, MINB)                                                                                            \
+#define MAD_FAST_LAUNCH(WY, MINB, PF)                                                                                        \
   do {                                                                                                                       \
     const int zc = fast_zc(L.g, WY);                                                                                         \
     const dim3 fg = fast_grid(L.g, WY, zc);                                                                                  \
-    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc); \
+    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc); \
     return (size_t)fg.x * fg.y * fg.z;                                                                                       \
   } while (0)
   if (sizeof(T) == 8) {
-    if (ctx->fast_cfg == 1) MAD_FAST_LAUNCH(8, 1);
-    MAD_FAST_LAUNCH(4, 2);
+    if (ctx->fast_cfg == 4) MAD_FAST_LAUNCH(4, 2, true);
+    MAD_FAST_LAUNCH(4, 2, false);
   }
   switch (ctx->fast_cfg) {
-    case 1: MAD_FAST_LAUNCH(8, 1);
-    case 2: MAD_FAST_LAUNCH(8, 2);
-    case 3: MAD_FAST_LAUNCH(4, 4);
-    default: MAD_FAST_LAUNCH(4, 3);
+    case 1: MAD_FAST_LAUNCH(8, 1, false);
+    case 4: MAD_FAST_LAUNCH(4, 2, true);
+    case 5: MAD_FAST_LAUNCH(8, 1, true);
+    default: MAD_FAST_LAUNCH(4, 3, false);
   }
 #undef MAD_FAST_LAUNCH
 }
@@ -233,6 +237,17 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
       if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega);
       else if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       else k_jacobi<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
+      std::swap(L.u, L.tmp);
+    } else if (use_fast(ctx, L) && ctx->gs_fused) {
+      // one pass: z-ordered planes, four in-plane colours, exact inside a CTA tile (mad_fast.cuh)
+      Scope s(ctx, cls);
+      if (ctx->fast_cfg == 1) {
+        const int zc = fast_zc(L.g, 8);
+        fast::k_fast_gs<8, 1><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc);
+      } else {
+        const int zc = fast_zc(L.g, 4);
+        fast::k_fast_gs<4, 3><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc);
+      }
       std::swap(L.u, L.tmp);
     } else {
       const int nc = ctx->dim == 2 ? 4 : (ctx->p.gs_colors == 8 ? 8 : 4);
@@ -839,6 +854,8 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   {
     const char* e = getenv("MADGPU_FAST_MIN_NX");  // test hook: 0 forces the streaming kernels on every 3-D level
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
+    e = getenv("MADGPU_GS_FUSED");
+    ctx->gs_fused = e ? atoi(e) : 1;
     e = getenv("MADGPU_FAST_CFG");
     ctx->fast_cfg = e ? atoi(e) : 0;
   }
@@ -1122,6 +1139,19 @@ int madgpu_set_profiling(madgpu_ctx* ctx, int32_t on)
 {
   if (!ctx) return MADGPU_EINVAL;
   ctx->profiling = on;
+  return 0;
+}
+
+int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
+{
+  if (!ctx || !tile || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
+  const Level& L = ctx->lv[level];
+  if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
+    const int wy = ctx->fast_cfg == 1 ? 8 : 4;
+    tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
+  } else {
+    tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level
+  }
   return 0;
 }
 

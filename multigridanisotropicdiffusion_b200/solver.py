@@ -207,6 +207,12 @@ class MadSolver:
         self._check(self._lib.madgpu_cycles_end_f64(self._ctx, _ptr(out)), "cycles_end")
         return out
 
+    def gs_tile(self, level=0):
+        """(tx, ty, tz) of the fused Gauss-Seidel sweep on `level`, or None for one pass per colour."""
+        t = (C.c_int32 * 3)()
+        self._check(self._lib.madgpu_gs_tile(self._ctx, int(level), t), "gs_tile")
+        return None if t[0] == 0 else (t[0], t[1], t[2])
+
     def relres_history(self) -> np.ndarray:
         p = self.params
         h = np.full(p.number_of_steps * p.max_cycles, np.nan)

@@ -25,7 +25,7 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=lambda c: f"cfg{c}")
+@pytest.fixture(params=[0, 1, 4, 5], ids=lambda c: f"cfg{c}")
 def fast_env(request, monkeypatch):
     monkeypatch.setenv("MADGPU_FAST_MIN_NX", "0")
     monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param))
@@ -125,3 +125,68 @@ def test_fast_vcycle_weighted_jacobi(case, fast_env):
     r = o.vcycle(f.astype(np.float64), f.astype(np.float64), level=0)
     assert rel_l2(g, r) < 1e-5, rel_l2(g, r)
     s.close()
+
+
+# ---------------------------------------------------------------------------------- fused Gauss-Seidel
+GS_CASES = [
+    ((12, 14, 64), (1.0, 1.0, 1.0), 0.1),
+    ((10, 9, 130), (0.5, 0.25, 1.0), 0.05),      # two tiles along x, odd row count
+    ((21, 11, 140), (0.3125, 0.3125, 0.5), 0.1),  # several z chunks? (tile from gs_tile)
+    ((23, 25, 27), (0.3125, 0.3125, 0.5), 0.1),
+    ((9, 6, 131), (1.0, 0.7, 1.3), 0.1),
+]
+
+
+@pytest.fixture(params=[0, 1], ids=lambda c: f"cfg{c}")
+def gs_env(request, monkeypatch):
+    monkeypatch.setenv("MADGPU_FAST_MIN_NX", "0")
+    monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("case", GS_CASES)
+def test_fused_gs_sweep_is_the_documented_ordering(case, gs_env):
+    """One fused sweep == sequential Gauss-Seidel in the documented order (z planes; even rows: even x, odd x;
+    odd rows), tile-local, evaluated on the CPU with the oracle's explicit operator rows."""
+    from util import gs_tile_sweep
+    s, o = _mk(case, smoother=0)
+    tile = s.gs_tile(0)
+    assert tile is not None and tile[0] == 128
+    shape = case[0]
+    u, f = random_image(shape, seed=1), random_image(shape, seed=2)
+    S = o.stencil(0)
+    g1 = s.op_smooth(0, u, f, smoother=0, n_iter=1)
+    r1 = gs_tile_sweep(S, u.astype(np.float64), f.astype(np.float64), tile)
+    assert rel_l2(g1, r1) < 2e-6, rel_l2(g1, r1)
+    assert np.abs(g1 - r1).max() < 3e-5 * np.abs(r1).max()
+    g2 = s.op_smooth(0, u, f, smoother=0, n_iter=2)
+    r2 = gs_tile_sweep(S, r1, f.astype(np.float64), tile)
+    assert rel_l2(g2, r2) < 4e-6, rel_l2(g2, r2)
+    s.close()
+
+
+@pytest.mark.parametrize("case", CASES_MG)
+def test_fused_gs_converged_image(case, gs_env):
+    """north_star: Gauss-Seidel within 1e-4 relative L2 on the converged diffused image (the reference sweeps
+    lexicographically; only the fixed point is comparable)."""
+    import multigridanisotropicdiffusion_b200 as M
+    from oracle import oracle as O
+    shape, sp, dt = case
+    T = random_spd_tensor(shape, seed=3)
+    img = random_image(shape, seed=4)
+    f = M.MultigridAnisotropicDiffusionImageFilter("gs")
+    f.SetInput(img, sp)
+    f.SetDiffusionTensor(T)
+    f.SetTimeStep(dt)
+    f.SetIterationsPerGrid(2)
+    f.SetTolerance(1e-9)
+    f.SetNumberOfSteps(2)
+    f.Update()
+    out = f.GetOutput().astype(np.float64)
+    st = f.stats
+    f.close()
+    o = O.Oracle(shape, sp, T.astype(np.float64), dt, smoother=0, nu=2)
+    ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-9, number_of_steps=2)
+    assert rel_l2(out, ref) < 1e-4, rel_l2(out, ref)
+    assert max(st["final_relres"][:2]) <= 1e-9
+    assert max(st["cycles_per_step"][:2]) <= max(cyc) + 2, (st["cycles_per_step"], cyc)

@@ -70,3 +70,40 @@ def load_ved_test():
     """69x77x69 int16 volume of the reference's test/test_data/ved_test.mhd/.zraw, spacing (.3125,.3125,.5)."""
     z = np.load(os.path.join(GOLDEN, "ved_test_i16.npz"))
     return z["image"], tuple(float(s) for s in z["spacing"])
+
+
+def gs_tile_sweep(S, u, f, tile):
+    """CPU model (numpy, explicit operator rows `S` from the oracle) of the fused GPU Gauss-Seidel sweep:
+    tiles of (tx, ty, tz) voxels; inside a tile planes in z order, each plane as even rows (even x, odd x)
+    then odd rows; values outside the tile are those of the previous sweep.  3-D only."""
+    TX, TY, TZ = tile
+    nz, ny, nx = u.shape
+    offs = [(ox, oy, oz) for oz in (-1, 0, 1) for oy in (-1, 0, 1) for ox in (-1, 0, 1)]
+    diag = S[..., 13]
+    old = np.zeros((nz + 2, ny + 2, nx + 2))
+    old[1:-1, 1:-1, 1:-1] = u
+    w = old.copy()
+    tx = np.arange(-1, nx + 1) // TX
+    ty = np.arange(-1, ny + 1) // TY
+    tz = np.arange(-1, nz + 1) // TZ
+    for z in range(nz):
+        for (cy, cx) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+            ys = np.arange(cy, ny, 2)
+            xs = np.arange(cx, nx, 2)
+            if len(ys) == 0 or len(xs) == 0:
+                continue
+            acc = np.zeros((len(ys), len(xs)))
+            Sz = S[z][np.ix_(ys, xs)]
+            for k, (ox, oy, oz) in enumerate(offs):
+                if (ox, oy, oz) == (0, 0, 0):
+                    continue
+                a = Sz[..., k]
+                if not a.any():
+                    continue
+                zz = z + oz
+                same = (tz[1 + zz] == tz[1 + z]) & (ty[1 + ys + oy] == ty[1 + ys])[:, None] & (tx[1 + xs + ox] == tx[1 + xs])[None, :]
+                vw = w[1 + zz][np.ix_(1 + ys + oy, 1 + xs + ox)]
+                vo = old[1 + zz][np.ix_(1 + ys + oy, 1 + xs + ox)]
+                acc += a * np.where(same, vw, vo)
+            w[1 + z][np.ix_(1 + ys, 1 + xs)] = (f[z][np.ix_(ys, xs)] - acc) / diag[z][np.ix_(ys, xs)]
+    return w[1:-1, 1:-1, 1:-1].copy()
