@@ -214,6 +214,36 @@ __device__ __forceinline__ void store4(OT* __restrict__ base, int o, int xt, int
   }
 }
 
+// L2 prefetch of the rows a warp will need `dist` planes ahead: the marching state leaves room for only
+// ~12 warps per SM, far too few to cover DRAM latency with loads that have a register destination, so the
+// HBM fetch is started early with prefetch.global.L2 (no destination) and the real loads hit L2.
+// One instruction per plane step covers the warp's 128-voxel row of all eight fp32 fields (u, f, six tensor
+// planes): lane = field * 4 + 128-byte line.  fp64 fields (level-0 outer residual) need a second one.
+struct Prefetch {
+  const char* a;     // lanes 0..31: field (lane >> 2), line (lane & 3)
+  const char* b;     // second half of the 1 KB rows of fp64 fields (null for fp32 fields)
+  long long stride;  // bytes per plane of this lane's field
+};
+template <typename UT, typename FT>
+__device__ __forceinline__ Prefetch make_prefetch(const Geom& g, const Tensor& D, const UT* u, const FT* f, int lane, int y)
+{
+  const int fid = lane >> 2, ln = lane & 3;
+  const size_t es = fid == 0 ? sizeof(UT) : fid == 1 ? sizeof(FT) : 4;
+  const char* base = fid == 0 ? reinterpret_cast<const char*>(u) : fid == 1 ? reinterpret_cast<const char*>(f)
+                                                                           : reinterpret_cast<const char*>(D.p[fid - 2]);
+  Prefetch P;
+  P.a = base + ((size_t)y * g.pitch + (size_t)blockIdx.x * TX) * es + ln * 128;
+  P.b = es == 8 ? P.a + 512 : nullptr;
+  P.stride = g.plane * (long long)es;
+  return P;
+}
+__device__ __forceinline__ void prefetch_plane(const Prefetch& P, int z)
+{
+  const char* q = P.a + P.stride * z;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  if (P.b) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b + P.stride * z));
+}
+
 __device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 
@@ -407,7 +437,7 @@ enum { MODE_WJ = 0, MODE_RES = 1 };
 // registers) instead of at the top of step z+1.
 template <int MODE, typename T, typename UT, typename FT, typename OT, int WY, int MINB, bool PF>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, const UT* __restrict__ u, const FT* __restrict__ f,
-                                                         OT* __restrict__ out, double* __restrict__ partials, float omega, int zc)
+                                                         OT* __restrict__ out, double* __restrict__ partials, float omega, int zc, int pfd)
 {
   const Pos p = make_pos(g);
   const bool valid = p.y < g.ny;
@@ -415,6 +445,8 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
   if (valid) {
     const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
     const int rowo = p.y * g.pitch + p.xl;
+    const Prefetch PFL = make_prefetch(g, D, u, f, p.lane, p.y);
+    const int zpf_end = min(z1 + 1, g.nz);  // planes 0..nz-1 exist for every field
     const T om = T(omega), om1 = T(1) - T(omega);
     UPlane<T> um, uc, up;
     DzState S;
@@ -432,6 +464,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 #pragma unroll 2
     for (int z = z0; z < z1; ++z) {
       const int oc = z * (int)g.plane + rowo;
+      if (pfd > 0 && z + pfd < zpf_end) prefetch_plane(PFL, z + pfd);
       if (!PF) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z);
       // ---- consume the loads issued one step ago ----
       finish_u<T, UT>(R.u, p, up);
@@ -486,7 +519,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 // ------------------------------------------------------------------------------------------
 template <int WY, int MINB>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, const float* __restrict__ u, const float* __restrict__ f,
-                                                             float* __restrict__ out, int zc)
+                                                             float* __restrict__ out, int zc, int pfd)
 {
   static_assert(WY % 2 == 0, "row colours alternate with the warp index");
   __shared__ float4 sh[2][WY][32];
@@ -497,6 +530,8 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
   const bool has_m = wm >= 0 && wm < WY, has_p = wp >= 0 && wp < WY && blockIdx.y * WY + wp < g.ny;
   const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
   const int rowo = (valid ? p.y : 0) * g.pitch + p.xl;
+  const Prefetch PFL = make_prefetch(g, D, u, f, p.lane, valid ? p.y : 0);
+  const int zpf_end = min(z1 + 1, g.nz);
   UPlane<float> um, uc, up;
   DzState S;
   {
@@ -511,6 +546,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
   for (int z = z0; z < z1; ++z) {
     const int oc = z * (int)g.plane + rowo;
     const int cb = z & 1, pb = cb ^ 1;
+    if (pfd > 0 && z + pfd < zpf_end) prefetch_plane(PFL, z + pfd);
     const StepRaw<float, float> R = issue_step<float, float>(g, D, u, f, p, rowo, z);
     finish_u<float, float>(R.u, p, up);
     S.xz_p = finish6<float, float>(R.dz.xz, p); S.yz_p = finish4<float>(R.dz.yz); S.zz_p = finish4<float>(R.dz.zz);
@@ -574,6 +610,119 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
     S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
     S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Inter-grid transfers, 4 fine voxels per thread along x.
+// ------------------------------------------------------------------------------------------
+
+// fine += P coarse (ADD) / fine = P coarse: gather form of Interpolation (mad/itkInterGridOperators.hxx:45-172,
+// tables .h:101-113) fused with the correction add of the V-cycle (…Filter.hxx:424-435).
+// The four fine voxels 4t..4t+3 of a thread interpolate from the coarse voxels 2t-1..2t+2 of up to four
+// coarse rows: 3 loads per coarse row (one 8-byte pair + two scalars), one 16-byte load/store of the fine row.
+// grid = (ceil(nxf/128), ceil(nyf/WY), nzf), block = (32, WY).
+template <bool ADD, int WY>
+__global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Transfer t, const float* __restrict__ coarse, float* __restrict__ fine)
+{
+  const int lane = threadIdx.x;
+  const int xt = blockIdx.x * TX + lane * 4;
+  const int y = blockIdx.y * WY + threadIdx.y;
+  const int z = blockIdx.z;
+  if (xt >= gf.nx || y >= gf.ny) return;
+  int y0, y1, z0, z1;
+  float wy0, wy1, wz0, wz1;
+  prolong_taps(y, gf.ny, gc.ny, t.cent[1], y0, y1, wy0, wy1);
+  prolong_taps(z, gf.nz, gc.nz, t.cent[2], z0, z1, wz0, wz1);
+  // x taps of the four fine voxels as weights on the coarse voxels cb..cb+3, cb = 2t-1
+  const int cb = (xt >> 1) - 1;
+  float W[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int i0, i1;
+    float w0, w1;
+    prolong_taps(xt + j, gf.nx, gc.nx, t.cent[0], i0, i1, w0, w1);
+    if (xt + j >= gf.nx) { w0 = 0.f; w1 = 0.f; i0 = i1 = cb + 1; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) W[j][k] = (i0 - cb == k ? w0 : 0.f) + (i1 - cb == k ? w1 : 0.f);
+  }
+  const int xa = max(cb, 0), xd = min(cb + 3, gc.nx - 1);            // clamped (their weights are zero when clamped)
+  const int xb = cb + 1, xc = min(cb + 2, gc.nx - 1);               // cb+1 = 2t is always a valid, 8-byte aligned voxel
+  const bool pair = xb + 1 < gc.nx;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int yy = (r & 1) ? y1 : y0, zz = (r & 2) ? z1 : z0;
+    const float wr = ((r & 1) ? wy1 : wy0) * ((r & 2) ? wz1 : wz0);
+    // no early-out on wr == 0: the tap rows are always valid, and branch-free code lets all twelve loads issue together
+    const float* row = coarse + (long long)zz * gc.plane + (long long)yy * gc.pitch;
+    float c[4];
+    c[0] = __ldg(row + xa);
+    if (pair) { const float2 q = __ldg(reinterpret_cast<const float2*>(row + xb)); c[1] = q.x; c[2] = q.y; }
+    else { c[1] = __ldg(row + xb); c[2] = __ldg(row + xc); }
+    c[3] = __ldg(row + xd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] += wr * (W[j][0] * c[0] + W[j][1] * c[1] + W[j][2] * c[2] + W[j][3] * c[3]);
+  }
+  const int o = z * (int)gf.plane + y * gf.pitch + xt;
+  if (ADD) {
+    const float4 q = *reinterpret_cast<const float4*>(fine + o);
+    acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+  }
+  store4<float>(fine, o, xt, gf.nx, acc);
+}
+
+// coarse = R fine: full weighting (mad/itkInterGridOperators.hxx:175-304, tables .h:115-127).  A thread reads
+// the fine voxels 4t-1..4t+4 of each contributing fine row (one 16-byte load + two shuffles) and produces the
+// coarse voxels 2t, 2t+1 (one 8-byte store); a warp covers 128 fine = 64 coarse voxels of one coarse row.
+// grid = (ceil(nxf/128), ceil(nyc/WY), nzc), block = (32, WY).
+template <int WY>
+__global__ void __launch_bounds__(32 * WY) k_fast_restrict(Geom gf, Geom gc, Transfer t, const float* __restrict__ fine, float* __restrict__ coarse)
+{
+  Pos p;
+  p.lane = threadIdx.x;
+  p.xt = blockIdx.x * TX + p.lane * 4;
+  p.xl = p.xt < gf.nx ? p.xt : 0;
+  p.edge = p.lane == 0 || p.lane == 31;
+  p.dh = (p.lane == 0 ? max(p.xt - 1, 0) : min(p.xt + 4, gf.nx - 1)) - p.xl;
+  const int yc = blockIdx.y * WY + threadIdx.y;
+  const int zc = blockIdx.z;
+  if (yc >= gc.ny) return;  // whole warp
+  float wy[4], wz[4], wxa[4], wxb[4];
+  restrict_taps(yc, gc.ny, t.cent[1], wy);
+  restrict_taps(zc, gc.nz, t.cent[2], wz);
+  const int xc0 = p.xt >> 1;  // coarse voxels xc0, xc0+1
+  restrict_taps(min(xc0, gc.nx - 1), gc.nx, t.cent[0], wxa);
+  restrict_taps(min(xc0 + 1, gc.nx - 1), gc.nx, t.cent[0], wxb);
+  float a0 = 0.f, a1 = 0.f;
+  // All sixteen tap rows are loaded unconditionally (rows outside the image are clamped and carry weight 0):
+  // branch-free, so the loads are issued back to back.
+  Raw6<float> raw[4][4];
+#pragma unroll
+  for (int kz = 0; kz < 4; ++kz) {
+    const int fz = min(max(2 * zc + kz - 1, 0), gf.nz - 1);
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int fy = min(max(2 * yc + ky - 1, 0), gf.ny - 1);
+      raw[kz][ky] = issue6(fine, fz * (int)gf.plane + fy * gf.pitch + p.xl, p);
+    }
+  }
+#pragma unroll
+  for (int kz = 0; kz < 4; ++kz) {
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const float wr = wy[ky] * wz[kz];
+      const V6<float> v = finish6<float, float>(raw[kz][ky], p);
+      // voxels beyond the fine row only ever meet zero weights, but may hold anything: mask them
+      float m[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const int fx = p.xt - 1 + k; m[k] = (fx >= 0 && fx < gf.nx) ? v.v[k] : 0.f; }
+      a0 += wr * (wxa[0] * m[0] + wxa[1] * m[1] + wxa[2] * m[2] + wxa[3] * m[3]);
+      a1 += wr * (wxb[0] * m[2] + wxb[1] * m[3] + wxb[2] * m[4] + wxb[3] * m[5]);
+    }
+  }
+  const long long o = (long long)zc * gc.plane + (long long)yc * gc.pitch + xc0;
+  if (xc0 + 1 < gc.nx) *reinterpret_cast<float2*>(coarse + o) = make_float2(a0, a1);
+  else if (xc0 < gc.nx) coarse[o] = a0;
 }
 
 }  // namespace fast

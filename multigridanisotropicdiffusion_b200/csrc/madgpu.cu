@@ -75,6 +75,7 @@ struct madgpu_ctx {
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   int64_t launches;
+  int pf_dist;      // L2 prefetch distance (planes) of the streaming kernels, 0 = off
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
@@ -144,7 +145,7 @@ size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT
   do {                                                                                                                       \
     const int zc = fast_zc(L.g, WY);                                                                                         \
     const dim3 fg = fast_grid(L.g, WY, zc);                                                                                  \
-    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc); \
+    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc, ctx->pf_dist); \
     return (size_t)fg.x * fg.y * fg.z;                                                                                       \
   } while (0)
   if (sizeof(T) == 8) {
@@ -243,10 +244,10 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
       Scope s(ctx, cls);
       if (ctx->fast_cfg == 1) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc);
+        fast::k_fast_gs<8, 1><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc);
+        fast::k_fast_gs<4, 3><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       }
       std::swap(L.u, L.tmp);
     } else {
@@ -327,6 +328,14 @@ void op_restrict(madgpu_ctx* ctx, int lf, const TI* fine, float* coarse, int cls
   const dim3 b = ctx->dim == 3 ? dim3(32, 4, 2) : dim3(32, 8, 1);
   const dim3 g = grid3(C.g, b);
   Scope s(ctx, cls);
+  if constexpr (std::is_same<TI, float>::value) {
+    if (use_fast(ctx, F) && F.g.nx >= 8) {
+      constexpr int WY = 8;
+      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (C.g.ny + WY - 1) / WY, C.g.nz);
+      fast::k_fast_restrict<WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(F.g, C.g, transfer_of(C), fine, coarse);
+      return;
+    }
+  }
   if (ctx->dim == 3) k_restrict<3, TI, float><<<g, b, 0, ctx->stream>>>(F.g, C.g, transfer_of(C), fine, coarse);
   else k_restrict<2, TI, float><<<g, b, 0, ctx->stream>>>(F.g, C.g, transfer_of(C), fine, coarse);
 }
@@ -339,6 +348,14 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
   const dim3 b = ctx->dim == 3 ? dim3(32, 4, 2) : dim3(32, 8, 1);
   const dim3 g = grid3(F.g, b);
   Scope s(ctx, MADGPU_K_PROLONG);
+  if constexpr (std::is_same<TO, float>::value) {
+    if (use_fast(ctx, F)) {
+      constexpr int WY = 8;
+      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, F.g.nz);
+      fast::k_fast_prolong<ADD, WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
+      return;
+    }
+  }
   if (ctx->dim == 3) k_prolong<3, TO, ADD><<<g, b, 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
   else k_prolong<2, TO, ADD><<<g, b, 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
 }
@@ -854,6 +871,8 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   {
     const char* e = getenv("MADGPU_FAST_MIN_NX");  // test hook: 0 forces the streaming kernels on every 3-D level
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
+    e = getenv("MADGPU_PF_DIST");
+    ctx->pf_dist = e ? atoi(e) : 2;
     e = getenv("MADGPU_GS_FUSED");
     ctx->gs_fused = e ? atoi(e) : 1;
     e = getenv("MADGPU_FAST_CFG");

@@ -190,3 +190,25 @@ def test_fused_gs_converged_image(case, gs_env):
     assert rel_l2(out, ref) < 1e-4, rel_l2(out, ref)
     assert max(st["final_relres"][:2]) <= 1e-9
     assert max(st["cycles_per_step"][:2]) <= max(cyc) + 2, (st["cycles_per_step"], cyc)
+
+
+@pytest.mark.parametrize("case", CASES + [((20, 22, 260), (1.0, 1.0, 1.0), 0.1), ((17, 19, 257), (1.0, 1.0, 1.0), 0.1)])
+def test_fast_restriction_and_prolongation(case, fast_env):
+    """Streaming transfer kernels (4 fine voxels per thread) against the oracle, every centring combination."""
+    from oracle import oracle as O
+    s, o = _mk(case)
+    for l in range(s.nlevels - 1):
+        cent = s.levels[l + 1]["centering"]
+        fine = random_image(s.levels[l]["shape"], seed=l + 11)
+        g = s.op_restrict(l, fine)
+        r = O.restrict(fine.astype(np.float64), cent)
+        assert g.shape == r.shape
+        assert rel_l2(g, r) < 3e-7, (l, rel_l2(g, r))
+        assert np.abs(g - r).max() < 1e-6 * np.abs(r).max()
+        coarse = random_image(s.levels[l + 1]["shape"], seed=l + 21)
+        gp = s.op_prolong(l, coarse)
+        rp = O.interpolate(coarse.astype(np.float64), cent)
+        assert gp.shape == rp.shape
+        assert rel_l2(gp, rp) < 3e-7, (l, rel_l2(gp, rp))
+        assert np.abs(gp - rp).max() < 1e-6 * np.abs(rp).max()
+    s.close()
