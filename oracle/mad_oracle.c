@@ -7,9 +7,16 @@
  * (libmadgpu.so) never calls into this file.
  *
  * Parity pin: the reference ships no golden vectors (its tests return EXIT_SUCCESS
- * unconditionally, test/itk2DDiffusionTest_WJ.cxx:151).  This restatement is pinned by
- * oracle/_ref (the UNMODIFIED reference headers compiled against oracle/shim, see
- * oracle/Makefile) -- tests/test_oracle_vs_ref.py compares the two on every entry point.
+ * unconditionally, test/itk2DDiffusionTest_WJ.cxx:151), so this restatement is pinned against
+ * the reference's OWN CODE: oracle/_ref/libmadref.so is the unmodified /root/reference/include
+ * headers compiled against the stand-in ITK/vnl of oracle/shim (oracle/Makefile, `make ref`).
+ *   - tests/test_oracle_vs_ref.py compares every routine and whole GenerateData() runs: operator
+ *     rows, smoothers, residual, transfers and direct solve agree bit for bit; whole solves agree in
+ *     cycle counts, per-cycle relative residuals and image (<= 1e-13).
+ *   - tests/test_cpu_golden.py compares with vectors recorded from that library
+ *     (tests/golden/make_golden.py) for the reference's three test programs, so the pin also holds
+ *     where oracle/_ref cannot be built (no /root/reference).
+ * The one third-party routine, vnl_sparse_lu, is an exact solve; here and in the shim it is a dense LU.
  *
  * Every function cites the reference file:line it follows.  Paths are relative to
  * /root/reference/include.  Arrays are x-fastest (ITK index[0] contiguous).
