@@ -1,6 +1,6 @@
 /*
  * mini_itk.h -- a minimal stand-in for the parts of ITK and VXL/vnl that the reference's solver headers
- * (/root/reference/include/itkMultigridAnisotropicDiffusionImageFilter.{h,hxx} and include/mad/*) use, so
+ * (/root/reference/include/itkMultigridAnisotropicDiffusionImageFilter.{h,hxx} and the include/mad headers) use, so
  * that those headers compile UNMODIFIED, where they lie, into oracle/_ref/libmadref.so (oracle/Makefile,
  * target `ref`).  TEST INFRASTRUCTURE ONLY: it exists to pin oracle/mad_oracle.c against the reference's own
  * code; nothing in the product links it.
@@ -188,12 +188,17 @@ private:
   T m_v[InternalDimension];
 };
 
+template <unsigned int D>
+struct SizeOf {  // Neighborhood has a member function called Size(); name the type from outside
+  typedef Size<D> Type;
+};
+
 template <typename T, unsigned int D>
 class Neighborhood
 {
 public:
-  typedef Size<D> SizeType;
-  typedef Size<D> RadiusType;
+  typedef typename SizeOf<D>::Type SizeType;
+  typedef typename SizeOf<D>::Type RadiusType;
   typedef Offset<D> OffsetType;
   typedef SizeValueType NeighborIndexType;
   Neighborhood() { m_Radius.Fill(0); m_Side.Fill(1); }
