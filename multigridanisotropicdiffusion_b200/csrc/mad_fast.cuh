@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 // New values travel: own row -> registers; x-neighbours -> warp shuffles; rows y+-1 of the plane
 // being updated and of the plane below -> shared memory (two row buffers, alternating with z).
 // ------------------------------------------------------------------------------------------
-template <int WY, int MINB>
+template <int WY, int MINB, bool PF>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, const float* __restrict__ u, const float* __restrict__ f,
                                                              float* __restrict__ out, int zc, int pfd)
 {
@@ -543,15 +543,20 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
     S.xz_m = finish4<float>(d0.xz.c); S.yz_m = finish4<float>(d0.yz); S.zz_m = finish4<float>(d0.zz);
     S.xz_c = finish6<float, float>(d1.xz, p); S.yz_c = finish4<float>(d1.yz); S.zz_c = finish4<float>(d1.zz);
   }
+  StepRaw<float, float> R;
+  if (PF) R = issue_step<float, float>(g, D, u, f, p, rowo, z0);
+#pragma unroll 2
   for (int z = z0; z < z1; ++z) {
     const int oc = z * (int)g.plane + rowo;
     const int cb = z & 1, pb = cb ^ 1;
     if (pfd > 0 && z + pfd < zpf_end) prefetch_plane(PFL, z + pfd);
-    const StepRaw<float, float> R = issue_step<float, float>(g, D, u, f, p, rowo, z);
+    if (!PF) R = issue_step<float, float>(g, D, u, f, p, rowo, z);
     finish_u<float, float>(R.u, p, up);
     S.xz_p = finish6<float, float>(R.dz.xz, p); S.yz_p = finish4<float>(R.dz.yz); S.zz_p = finish4<float>(R.dz.zz);
     const DcFin F = finish_dc(R.dc, p);
     const V4<float> fv = finish4<float>(R.f);
+    // software pipelining: the loads of the next plane fly while this plane's two phases run
+    if (PF && z + 1 < z1) R = issue_step<float, float>(g, D, u, f, p, rowo, z + 1);
     Coef<float> c;
     coefficients<float>(g, D, p, z, oc, S, F, c);
     // plane z-1 was updated one step ago: rows y+-1 come from the tile's row buffer (own row: registers)

@@ -244,10 +244,19 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
       Scope s(ctx, cls);
       if (ctx->fast_cfg == 1) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<8, 1, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+      } else if (ctx->fast_cfg == 4) {
+        const int zc = fast_zc(L.g, 4);
+        fast::k_fast_gs<4, 2, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+      } else if (ctx->fast_cfg == 5) {
+        const int zc = fast_zc(L.g, 8);
+        fast::k_fast_gs<8, 1, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+      } else if (ctx->fast_cfg == 6) {
+        const int zc = fast_zc(L.g, 2);
+        fast::k_fast_gs<2, 6, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<4, 3, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       }
       std::swap(L.u, L.tmp);
     } else {
@@ -1166,7 +1175,7 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (!ctx || !tile || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
   const Level& L = ctx->lv[level];
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
-    const int wy = ctx->fast_cfg == 1 ? 8 : 4;
+    const int wy = (ctx->fast_cfg == 1 || ctx->fast_cfg == 5) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
     tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level
