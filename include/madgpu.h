@@ -112,6 +112,21 @@ int madgpu_create(const madgpu_params *p, madgpu_ctx **out);
 void madgpu_destroy(madgpu_ctx *ctx);
 const char *madgpu_last_error(const madgpu_ctx *ctx); /* ctx may be NULL: error of the last failed create */
 
+/* ---- z-slab decomposition over the GPUs of one node (new; the reference is single-process) ----
+ * One process (and one context) per GPU.  params.size is the GLOBAL volume, params.rank / world_size say which slab of
+ * z planes this context owns: size[2] / world_size consecutive planes, rank 0 lowest.  The finest levels stay
+ * distributed (one xy-plane halo per neighbour and sweep over NCCL send/recv on the solver's stream, one scalar
+ * all-reduce per norm); levels of 64^3 voxels or fewer are gathered onto rank 0, which runs the rest of the V-cycle
+ * and scatters the correction back.  Every entry point becomes a collective: all ranks call it with their own slab
+ * (images, tensor) in the same order.  Requirements: 3-D, size[2] divisible by world_size, planes per rank even
+ * and >= 4; FMG is not available.  NCCL is bound at run time (dlopen of libnccl.so.2).
+ *   id128: 128 bytes from madgpu_nccl_unique_id() on one rank, distributed by the caller (MPI, torch.distributed, ...). */
+int madgpu_nccl_unique_id(void *id128);
+int madgpu_create_slab(const madgpu_params *p, const void *nccl_unique_id, madgpu_ctx **out);
+/* planes [z_begin, z_begin + z_count) of `level` held by this context; global_nz = planes of the whole level.
+ * Valid for the levels this context holds (all of them when world_size == 1). */
+int madgpu_slab(const madgpu_ctx *ctx, int32_t level, int32_t *z_begin, int32_t *z_count, int32_t *global_nz);
+
 /* Run-time changes of the solver settings that do not alter the hierarchy
  * (itkSetMacro setters; time_step / size / spacing changes need a new context). */
 int madgpu_set_solver(madgpu_ctx *ctx, int32_t smoother, double omega, int32_t iterations_per_grid, int32_t cycle,

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Tran
   int y0, y1, z0, z1;
   float wy0, wy1, wz0, wz1;
   prolong_taps(y, gf.ny, gc.ny, t.cent[1], y0, y1, wy0, wy1);
-  prolong_taps(z, gf.nz, gc.nz, t.cent[2], z0, z1, wz0, wz1);
+  prolong_taps(z, gf.nz, gc.nz, t.cent[2], z0, z1, wz0, wz1, gf.zlo_phys != 0, gf.zhi_phys != 0);
   // x taps of the four fine voxels as weights on the coarse voxels cb..cb+3, cb = 2t-1
   const int cb = (xt >> 1) - 1;
   float W[4][4];
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict(Geom gf, Geom gc, Tra
   if (yc >= gc.ny) return;  // whole warp
   float wy[4], wz[4], wxa[4], wxb[4];
   restrict_taps(yc, gc.ny, t.cent[1], wy);
-  restrict_taps(zc, gc.nz, t.cent[2], wz);
+  restrict_taps(zc, gc.nz, t.cent[2], wz, gc.zlo_phys != 0, gc.zhi_phys != 0);
   const int xc0 = p.xt >> 1;  // coarse voxels xc0, xc0+1
   restrict_taps(min(xc0, gc.nx - 1), gc.nx, t.cent[0], wxa);
   restrict_taps(min(xc0 + 1, gc.nx - 1), gc.nx, t.cent[0], wxb);
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict(Geom gf, Geom gc, Tra
   Raw6<float> raw[4][4];
 #pragma unroll
   for (int kz = 0; kz < 4; ++kz) {
-    const int fz = min(max(2 * zc + kz - 1, 0), gf.nz - 1);
+    const int fz = min(max(2 * zc + kz - 1, gf.zlo_phys ? 0 : -1), gf.zhi_phys ? gf.nz - 1 : gf.nz);  // ghost planes of a z-slab are valid
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
       const int fy = min(max(2 * yc + ky - 1, 0), gf.ny - 1);

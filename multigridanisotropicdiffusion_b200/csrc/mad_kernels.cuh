@@ -308,14 +308,17 @@ struct Transfer {
 
 // Gather taps of full weighting along one axis for coarse index c: fine indices 2c-1..2c+2.
 // Tables: mad/itkInterGridOperators.h:115-127 (vertex ends are injection).
-__device__ __forceinline__ void restrict_taps(int c, int nc, int cent, float w[4])
+// lo / hi: the first / last index of this axis is a physical boundary (false at an inner face of a z-slab,
+// whose ghost planes hold the neighbour's values: interior weights apply there).
+__device__ __forceinline__ void restrict_taps(int c, int nc, int cent, float w[4], bool lo = true, bool hi = true)
 {
+  const bool first = c == 0 && lo, last = c == nc - 1 && hi;
   if (cent == 0) {
-    if (c == 0 || c == nc - 1) { w[0] = 0.f; w[1] = 1.f; w[2] = 0.f; w[3] = 0.f; }
+    if (first || last) { w[0] = 0.f; w[1] = 1.f; w[2] = 0.f; w[3] = 0.f; }
     else { w[0] = .25f; w[1] = .5f; w[2] = .25f; w[3] = 0.f; }
   } else {
-    if (c == 0) { w[0] = 0.f; w[1] = .5f; w[2] = .375f; w[3] = .125f; }
-    else if (c == nc - 1) { w[0] = .125f; w[1] = .375f; w[2] = .5f; w[3] = 0.f; }
+    if (first) { w[0] = 0.f; w[1] = .5f; w[2] = .375f; w[3] = .125f; }
+    else if (last) { w[0] = .125f; w[1] = .375f; w[2] = .5f; w[3] = 0.f; }
     else { w[0] = .125f; w[1] = .375f; w[2] = .375f; w[3] = .125f; }
   }
 }
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(256) k_restrict(Geom gf, Geom gc, Transfer t, 
   float wx[4], wy[4], wz[4];
   restrict_taps(x, gc.nx, t.cent[0], wx);
   restrict_taps(y, gc.ny, t.cent[1], wy);
-  if (DIM == 3) restrict_taps(z, gc.nz, t.cent[2], wz);
+  if (DIM == 3) restrict_taps(z, gc.nz, t.cent[2], wz, gc.zlo_phys != 0, gc.zhi_phys != 0);
   typedef typename std::conditional<std::is_same<TI, double>::value, double, float>::type A;
   A acc = 0;
   constexpr int KZ = DIM == 3 ? 4 : 1;
@@ -358,15 +361,16 @@ __global__ void __launch_bounds__(256) k_restrict(Geom gf, Geom gc, Transfer t, 
 // Gather form of the reference's scatter interpolation along one axis: fine index x takes
 // w0*c[i0] + w1*c[i1].  vertex: f[2i]=c[i], f[2i+1]=(c[i]+c[i+1])/2.  cell: f[2i]=3/4 c[i]+1/4 c[i-1],
 // f[2i+1]=3/4 c[i]+1/4 c[i+1], f[0]=c[0], f[n-1]=c[nc-1]  (mad/itkInterGridOperators.h:101-113).
-__device__ __forceinline__ void prolong_taps(int x, int nf, int nc, int cent, int& i0, int& i1, float& w0, float& w1)
+__device__ __forceinline__ void prolong_taps(int x, int nf, int nc, int cent, int& i0, int& i1, float& w0, float& w1, bool lo = true,
+                                             bool hi = true)
 {
   const int i = x >> 1;
   if (cent == 0) {
     if ((x & 1) == 0) { i0 = i1 = i; w0 = 1.f; w1 = 0.f; }
     else { i0 = i; i1 = i + 1; w0 = .5f; w1 = .5f; }
   } else {
-    if (x == 0) { i0 = i1 = 0; w0 = 1.f; w1 = 0.f; }
-    else if (x == nf - 1) { i0 = i1 = nc - 1; w0 = 1.f; w1 = 0.f; }
+    if (x == 0 && lo) { i0 = i1 = 0; w0 = 1.f; w1 = 0.f; }
+    else if (x == nf - 1 && hi) { i0 = i1 = nc - 1; w0 = 1.f; w1 = 0.f; }
     else if ((x & 1) == 0) { i0 = i; i1 = i - 1; w0 = .75f; w1 = .25f; }
     else { i0 = i; i1 = i + 1; w0 = .75f; w1 = .25f; }
   }
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(256) k_prolong(Geom gc, Geom gf, Transfer t, c
   float wx0, wx1, wy0, wy1, wz0 = 1.f, wz1 = 0.f;
   prolong_taps(x, gf.nx, gc.nx, t.cent[0], x0, x1, wx0, wx1);
   prolong_taps(y, gf.ny, gc.ny, t.cent[1], y0, y1, wy0, wy1);
-  if (DIM == 3) prolong_taps(z, gf.nz, gc.nz, t.cent[2], z0, z1, wz0, wz1);
+  if (DIM == 3) prolong_taps(z, gf.nz, gc.nz, t.cent[2], z0, z1, wz0, wz1, gf.zlo_phys != 0, gf.zhi_phys != 0);
   const float* p00 = coarse + (long long)z0 * gc.plane + (long long)y0 * gc.pitch;
   const float* p01 = coarse + (long long)z0 * gc.plane + (long long)y1 * gc.pitch;
   float v = wy0 * (wx0 * p00[x0] + wx1 * p00[x1]) + wy1 * (wx0 * p01[x0] + wx1 * p01[x1]);

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <string>
 #include <vector>
 
@@ -38,10 +39,31 @@ struct Level {
   int n[3];
   double h[3];
   int cent[3];
+  int gnz;       // global number of planes of this level (== n[2] unless this context is one z-slab of it)
+  int zb;        // global z of local plane 0
   size_t elems;  // allocation size in elements (incl. 2 ghost planes)
   float *u, *f, *tmp;  // plane-0 pointers
   float* D[6];
   std::vector<void*> allocs;
+};
+
+// NCCL is bound at run time (dlopen): libmadgpu.so has no load-time dependency on it and single-GPU users never
+// touch it.  Only the handful of entry points the halo exchange needs are declared (ABI of nccl.h 2.x).
+struct Nccl {
+  typedef struct ncclComm* comm_t;
+  struct UniqueId { char internal[128]; };
+  enum { Float32 = 7, Float64 = 8, Sum = 0 };
+  void* lib;
+  int (*GetUniqueId)(UniqueId*);
+  int (*CommInitRank)(comm_t*, int, UniqueId, int);
+  int (*CommDestroy)(comm_t);
+  int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t);
+  int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t);
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t);
+  int (*Broadcast)(const void*, void*, size_t, int, int, comm_t, cudaStream_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  const char* (*GetErrorString)(int);
 };
 
 struct ProfEvent {
@@ -75,6 +97,17 @@ struct madgpu_ctx {
   std::vector<ProfEvent> prof;
   std::vector<cudaEvent_t> ev_pool;
   int64_t launches;
+  // z-slab decomposition (world > 1): this context owns planes [lv[l].zb, lv[l].zb + lv[l].n[2]) of levels 0..nlevels-1;
+  // the last of them (the agglomeration level) is gathered to rank 0, whose `sub` context holds the rest of the hierarchy
+  int rank, world;
+  std::string sticky;  // first collective error inside an operator
+  bool borrowed_stream;  // sub-context of a slab context: runs on the parent's stream
+  Nccl::comm_t comm;
+  madgpu_ctx* sub;
+  float* gather_buf;   // rank 0: dense agglomeration-level field (all slabs)
+  float* slab_buf;     // every rank: dense local slab of the agglomeration level, +2 ghost planes
+  int total_levels;    // levels of the whole hierarchy (distributed + serial)
+  int gsize[MADGPU_MAX_LEVELS][3], gcent[MADGPU_MAX_LEVELS][3];  // global level schedule
   int pf_dist;      // L2 prefetch distance (planes) of the streaming kernels, 0 = off
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
@@ -218,6 +251,129 @@ Tensor tensor_of(const Level& L)
   return t;
 }
 
+// ---- z-slab decomposition: NCCL binding, halo exchange, agglomeration ------------------------------
+Nccl g_nccl = {};
+
+const char* nccl_load()
+{
+  if (g_nccl.lib) return nullptr;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) return "libnccl.so.2 not found (needed only for world_size > 1)";
+#define MAD_SYM(field, name)                                             \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                             \
+  if (!g_nccl.field) return "libnccl lacks " name;
+  MAD_SYM(GetUniqueId, "ncclGetUniqueId")
+  MAD_SYM(CommInitRank, "ncclCommInitRank")
+  MAD_SYM(CommDestroy, "ncclCommDestroy")
+  MAD_SYM(Send, "ncclSend")
+  MAD_SYM(Recv, "ncclRecv")
+  MAD_SYM(AllReduce, "ncclAllReduce")
+  MAD_SYM(Broadcast, "ncclBroadcast")
+  MAD_SYM(GroupStart, "ncclGroupStart")
+  MAD_SYM(GroupEnd, "ncclGroupEnd")
+  MAD_SYM(GetErrorString, "ncclGetErrorString")
+#undef MAD_SYM
+  g_nccl.lib = h;
+  return nullptr;
+}
+
+// Collective errors inside the (void) operator functions are latched here and reported by the entry point.
+void latch(madgpu_ctx* ctx, int r, const char* what)
+{
+  if (r != 0 && ctx->sticky.empty()) ctx->sticky = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error");
+}
+#define NCV(call) latch(ctx, (call), #call)
+
+// Ghost planes of a level field: plane -1 <- last plane of rank-1, plane nz <- first plane of rank+1 (one ncclSend/Recv
+// pair per neighbour on the solver's stream).  The outer ranks keep their Neumann mirror handling (zlo_phys / zhi_phys).
+template <typename T>
+void exchange_halo(madgpu_ctx* ctx, const Level& L, T* field)
+{
+  if (ctx->world == 1) return;
+  Scope s(ctx, MADGPU_K_HALO, 0);
+  const size_t cnt = (size_t)L.g.plane * (sizeof(T) / sizeof(float));
+  float* f = reinterpret_cast<float*>(field);
+  const size_t pl = (size_t)L.g.plane * (sizeof(T) / sizeof(float));
+  NCV(g_nccl.GroupStart());
+  if (ctx->rank > 0) {
+    NCV(g_nccl.Send(f, cnt, Nccl::Float32, ctx->rank - 1, ctx->comm, ctx->stream));
+    NCV(g_nccl.Recv(f - pl, cnt, Nccl::Float32, ctx->rank - 1, ctx->comm, ctx->stream));
+  }
+  if (ctx->rank < ctx->world - 1) {
+    NCV(g_nccl.Send(f + (size_t)(L.g.nz - 1) * pl, cnt, Nccl::Float32, ctx->rank + 1, ctx->comm, ctx->stream));
+    NCV(g_nccl.Recv(f + (size_t)L.g.nz * pl, cnt, Nccl::Float32, ctx->rank + 1, ctx->comm, ctx->stream));
+  }
+  NCV(g_nccl.GroupEnd());
+}
+
+// dense slab <-> pitched field of the agglomeration level
+void pack_slab(madgpu_ctx* ctx, const Level& L, const float* pitched, float* dense)
+{
+  const dim3 b = block3(3), g = grid3(L.g, b);
+  k_pitched_to_dense<float, float><<<g, b, 0, ctx->stream>>>(L.g, pitched, dense);
+  ctx->launches++;
+}
+void unpack_slab(madgpu_ctx* ctx, const Level& L, const float* dense, float* pitched)
+{
+  const dim3 b = block3(3), g = grid3(L.g, b);
+  k_dense_to_pitched<float, float><<<g, b, 0, ctx->stream>>>(L.g, dense, pitched);
+  ctx->launches++;
+}
+
+// every rank's dense slab (slab_buf) -> rank 0's dense global field (gather_buf); equal slab sizes
+void gather_slabs(madgpu_ctx* ctx, const Level& L)
+{
+  const size_t cnt = (size_t)L.n[0] * L.n[1] * L.n[2];
+  NCV(g_nccl.GroupStart());
+  if (ctx->rank == 0) {
+    for (int r = 1; r < ctx->world; ++r) NCV(g_nccl.Recv(ctx->gather_buf + (size_t)r * cnt, cnt, Nccl::Float32, r, ctx->comm, ctx->stream));
+  } else {
+    NCV(g_nccl.Send(ctx->slab_buf, cnt, Nccl::Float32, 0, ctx->comm, ctx->stream));
+  }
+  NCV(g_nccl.GroupEnd());
+  if (ctx->rank == 0) cudaMemcpyAsync(ctx->gather_buf, ctx->slab_buf, cnt * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+}
+void scatter_slabs(madgpu_ctx* ctx, const Level& L)
+{
+  const size_t cnt = (size_t)L.n[0] * L.n[1] * L.n[2];
+  NCV(g_nccl.GroupStart());
+  if (ctx->rank == 0) {
+    for (int r = 1; r < ctx->world; ++r) NCV(g_nccl.Send(ctx->gather_buf + (size_t)r * cnt, cnt, Nccl::Float32, r, ctx->comm, ctx->stream));
+  } else {
+    NCV(g_nccl.Recv(ctx->slab_buf, cnt, Nccl::Float32, 0, ctx->comm, ctx->stream));
+  }
+  NCV(g_nccl.GroupEnd());
+  if (ctx->rank == 0) cudaMemcpyAsync(ctx->slab_buf, ctx->gather_buf, cnt * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+}
+
+void vcycle(madgpu_ctx* ctx, int l);
+void op_zero(madgpu_ctx* ctx, Level& L, float* p);
+
+// The agglomeration level (last level of a slab context): its right-hand side is gathered onto rank 0, which runs the
+// rest of the V-cycle on its serial sub-hierarchy, and the correction is scattered back.
+void agglomerated_solve(madgpu_ctx* ctx)
+{
+  Level& L = ctx->lv[ctx->nlevels - 1];
+  Scope s(ctx, MADGPU_K_COARSE, 0);
+  pack_slab(ctx, L, L.f, ctx->slab_buf);
+  gather_slabs(ctx, L);
+  if (ctx->rank == 0) {
+    madgpu_ctx* S = ctx->sub;
+    Level& S0 = S->lv[0];
+    unpack_slab(S, S0, ctx->gather_buf, S0.f);
+    op_zero(S, S0, S0.u);
+    vcycle(S, 0);
+    pack_slab(S, S0, S0.u, ctx->gather_buf);
+    ctx->launches += S->launches;
+    S->launches = 0;
+  }
+  scatter_slabs(ctx, L);
+  unpack_slab(ctx, L, ctx->slab_buf, L.u);
+}
+
 // ---- operators ----------------------------------------------------------------------------
 void op_zero(madgpu_ctx* ctx, Level& L, float* p)
 {
@@ -233,6 +389,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
   const int cls = l == 0 ? MADGPU_K_SMOOTH0 : MADGPU_K_SMOOTHC;
   const Tensor D = tensor_of(L);
   for (int it = 0; it < n_iter; ++it) {
+    exchange_halo(ctx, L, L.u);
     if (smoother == MADGPU_SMOOTHER_WJ) {
       Scope s(ctx, cls);
       if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega);
@@ -281,6 +438,7 @@ double read_scalar(madgpu_ctx* ctx)
 void reduce_partials(madgpu_ctx* ctx, size_t n)
 {
   k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(ctx->partials, (long long)n, ctx->d_scalar);
+  if (ctx->world > 1) NCV(g_nccl.AllReduce(ctx->d_scalar, ctx->d_scalar, 1, Nccl::Float64, Nccl::Sum, ctx->comm, ctx->stream));
 }
 
 // L.tmp = L.f - A L.u  (fp32)
@@ -288,6 +446,7 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
 {
   Level& L = ctx->lv[l];
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
+  exchange_halo(ctx, L, L.u);
   Scope s(ctx, MADGPU_K_RESTRICT, norm ? 2 : 1);
   const Tensor D = tensor_of(L);
   double* part = norm ? ctx->partials : nullptr;
@@ -306,6 +465,7 @@ void op_residual64(madgpu_ctx* ctx, float* r32_or_null, double* r64_or_null)
 {
   Level& L = ctx->lv[0];
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
+  exchange_halo(ctx, L, ctx->u64);
   Scope s(ctx, MADGPU_K_RESID0, 2);
   const Tensor D = tensor_of(L);
   if (r64_or_null) {
@@ -336,6 +496,7 @@ void op_restrict(madgpu_ctx* ctx, int lf, const TI* fine, float* coarse, int cls
   Level& C = ctx->lv[lf + 1];
   const dim3 b = ctx->dim == 3 ? dim3(32, 4, 2) : dim3(32, 8, 1);
   const dim3 g = grid3(C.g, b);
+  exchange_halo(ctx, F, const_cast<TI*>(fine));
   Scope s(ctx, cls);
   if constexpr (std::is_same<TI, float>::value) {
     if (use_fast(ctx, F) && F.g.nx >= 8) {
@@ -356,6 +517,7 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
   Level& C = ctx->lv[lf + 1];
   const dim3 b = ctx->dim == 3 ? dim3(32, 4, 2) : dim3(32, 8, 1);
   const dim3 g = grid3(F.g, b);
+  exchange_halo(ctx, C, const_cast<float*>(coarse));
   Scope s(ctx, MADGPU_K_PROLONG);
   if constexpr (std::is_same<TO, float>::value) {
     if (use_fast(ctx, F)) {
@@ -404,7 +566,8 @@ void op_coarse_solve(madgpu_ctx* ctx)
 void vcycle(madgpu_ctx* ctx, int l)
 {
   if (l == ctx->nlevels - 1) {  // :356-371
-    op_coarse_solve(ctx);
+    if (ctx->world > 1) agglomerated_solve(ctx);
+    else op_coarse_solve(ctx);
     return;
   }
   Level& L = ctx->lv[l];
@@ -498,6 +661,28 @@ int level_schedule(int dim, const int* n0, int sizes[][3], int cent[][3])
       else { sizes[l][d] = (nf - 1) / 2 + 1; cent[l][d] = 0; }
     }
   return nlev;
+}
+
+// z-slab plan.  Levels 0..La-1 are distributed: every rank owns gnz_l / world consecutive planes, slab
+// starts even at every level so that cell-centred transfers need a one-plane halo; level La is the agglomeration
+// level (each rank still holds its slab of it as the target of the last restriction, rank 0 gathers it and owns the
+// rest of the hierarchy).  Returns La (>= 1) or -1 when the volume cannot be cut this way.
+int plan_slabs(int nlev, const int sizes[][3], int world, std::string& why)
+{
+  if (nlev < 2) { why = "the volume has a single level, nothing to distribute"; return -1; }
+  if (sizes[0][2] % world != 0) { why = "size[2] must be divisible by world_size"; return -1; }
+  int lnz = sizes[0][2] / world;
+  int La = 0;
+  for (int l = 0; l + 1 < nlev; ++l) {
+    // can level l be distributed, i.e. can its slabs be restricted to slabs of level l+1?
+    const bool ok = sizes[l][2] % 2 == 0 && lnz % 2 == 0 && lnz >= 4;
+    const long long vox = (long long)sizes[l][0] * sizes[l][1] * sizes[l][2];
+    if (!ok || (l > 0 && vox <= 64ll * 64 * 64)) break;  // small levels are latency-bound: agglomerate
+    lnz /= 2;
+    La = l + 1;
+  }
+  if (La < 1) { why = "planes per rank must be even and >= 4 on the finest level"; return -1; }
+  return La;
 }
 
 void fill_geom(Level& L, int dim, double dt)
@@ -662,6 +847,28 @@ int finish_tensor(madgpu_ctx* ctx)
     for (int c = 0; c < ctx->ncomp; ++c)  // mad/itkGridsHierarchy.hxx:149-162
       op_restrict<float>(ctx, l, ctx->lv[l].D[c], ctx->lv[l + 1].D[c], MADGPU_K_MISC);
   CU(cudaGetLastError());
+  if (ctx->world > 1) {
+    // tensor of the agglomeration level -> rank 0, which finishes the hierarchy below it
+    Level& A = ctx->lv[ctx->nlevels - 1];
+    for (int c = 0; c < ctx->ncomp; ++c) {
+      pack_slab(ctx, A, A.D[c], ctx->slab_buf);
+      gather_slabs(ctx, A);
+      if (ctx->rank == 0) unpack_slab(ctx->sub, ctx->sub->lv[0], ctx->gather_buf, ctx->sub->lv[0].D[c]);
+    }
+    double flag = 0.0;
+    if (ctx->rank == 0) {
+      const int rc = finish_tensor(ctx->sub);
+      if (rc != 0) { ctx->err = ctx->sub->err; flag = (double)rc; }
+    }
+    // every rank must learn whether rank 0 could build the coarse hierarchy
+    CU(cudaMemcpyAsync(ctx->d_scalar, &flag, sizeof flag, cudaMemcpyHostToDevice, ctx->stream));
+    NCV(g_nccl.Broadcast(ctx->d_scalar, ctx->d_scalar, 1, Nccl::Float64, 0, ctx->comm, ctx->stream));
+    const double got = read_scalar(ctx);
+    if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
+    if (got != 0.0) return ctx->rank == 0 ? (int)got : fail(ctx, (int)got, "rank 0 could not build the agglomerated coarse hierarchy");
+    ctx->tensor_set = true;
+    return 0;
+  }
   const int rc = build_coarse_solver(ctx);
   if (rc != 0) return rc;
   ctx->tensor_set = true;
@@ -765,7 +972,7 @@ int run_steps(madgpu_ctx* ctx)
       outer_iteration(ctx, P.cycle == MADGPU_CYCLE_SMOOTHER);
       relres = std::sqrt(read_scalar(ctx)) / rhs_norm;
       ctx->relres_hist[(size_t)n * P.max_cycles + it] = relres;
-      if (P.verbose) {
+      if (P.verbose && ctx->rank == 0) {
         if (P.cycle == MADGPU_CYCLE_SMOOTHER) printf("Smoother iteration n. %d: relative residual = %g\n", it + 1, relres);
         else printf("|--- VCycle n. %d ---| relative residual = %g\n", it + 1, relres);
       }
@@ -784,6 +991,7 @@ int run_steps(madgpu_ctx* ctx)
   ctx->st.fmg_ms = fmg_ms_total;
   ctx->st.solve_ms = solve_ms_total;
   CU(cudaGetLastError());
+  if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
   return 0;
 }
 
@@ -793,7 +1001,7 @@ void begin_stats(madgpu_ctx* ctx)
   memset(&ctx->st, 0, sizeof ctx->st);
   ctx->st.struct_size = (int32_t)sizeof(madgpu_stats);
   ctx->st.setup_ms = setup;
-  ctx->st.levels = ctx->nlevels;
+  ctx->st.levels = ctx->total_levels;
   ctx->launches = 0;
 }
 
@@ -812,6 +1020,8 @@ int check_ready(madgpu_ctx* ctx)
   if (!ctx) return MADGPU_EINVAL;
   if (!ctx->tensor_set) return fail(ctx, MADGPU_ESTATE, "diffusion tensor not set (call madgpu_set_tensor_* first)");
   if (ctx->p.number_of_steps < 1) return fail(ctx, MADGPU_EINVAL, "number_of_steps must be >= 1");
+  if (ctx->world > 1 && ctx->p.cycle == MADGPU_CYCLE_FMG) return fail(ctx, MADGPU_ESTATE, "FMG is not available on a z-slab context (world_size > 1)");
+  if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
   return 0;
 }
 
@@ -845,7 +1055,38 @@ void madgpu_params_default(madgpu_params* p)
 
 const char* madgpu_last_error(const madgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t shared_stream, madgpu_ctx** out);
+
 int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
+{
+  if (p && p->struct_size == (int32_t)sizeof(madgpu_params) && p->world_size != 1)
+    return fail(nullptr, MADGPU_EINVAL, "world_size %d: use madgpu_create_slab (needs the NCCL unique id)", p->world_size);
+  return create_ctx(p, nullptr, nullptr, out);
+}
+
+int madgpu_nccl_unique_id(void* id128)
+{
+  if (!id128) return MADGPU_EINVAL;
+  const char* e = nccl_load();
+  if (e) return fail(nullptr, MADGPU_ECUDA, "%s", e);
+  Nccl::UniqueId id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail(nullptr, MADGPU_ECUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int madgpu_create_slab(const madgpu_params* p, const void* nccl_unique_id, madgpu_ctx** out)
+{
+  if (!p || !out || !nccl_unique_id) return fail(nullptr, MADGPU_EINVAL, "null argument");
+  if (p->struct_size != (int32_t)sizeof(madgpu_params)) return fail(nullptr, MADGPU_EINVAL, "madgpu_params size mismatch");
+  if (p->world_size < 1 || p->rank < 0 || p->rank >= p->world_size) return fail(nullptr, MADGPU_EINVAL, "bad rank %d / world_size %d", p->rank, p->world_size);
+  if (p->world_size == 1) return create_ctx(p, nullptr, nullptr, out);
+  if (p->dim != 3) return fail(nullptr, MADGPU_EINVAL, "z-slab decomposition needs a 3-D volume");
+  return create_ctx(p, nccl_unique_id, nullptr, out);
+}
+
+static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t shared_stream, madgpu_ctx** out)
 {
   madgpu_ctx* ctx = nullptr;  // errors before the context exists go to the thread-local slot
   if (!p || !out) return fail(ctx, MADGPU_EINVAL, "null argument");
@@ -860,7 +1101,7 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   if (p->smoother != MADGPU_SMOOTHER_GS && p->smoother != MADGPU_SMOOTHER_WJ) return fail(ctx, MADGPU_EINVAL, "unknown smoother %d", p->smoother);
   if (p->cycle < 0 || p->cycle > 2) return fail(ctx, MADGPU_EINVAL, "unknown cycle %d", p->cycle);
   if (p->max_cycles < 1) return fail(ctx, MADGPU_EINVAL, "max_cycles must be >= 1");
-  if (p->world_size != 1) return fail(ctx, MADGPU_EINVAL, "world_size %d: z-slab decomposition is driven by the host package (one context per rank)", p->world_size);
+  const int world = nccl_id ? p->world_size : 1, rank = nccl_id ? p->rank : 0;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(ctx, MADGPU_ECUDA, "no CUDA device: %s (libmadgpu has no CPU fallback)", cudaGetErrorString(e));
@@ -877,6 +1118,8 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
   ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
+  ctx->rank = rank; ctx->world = world; ctx->comm = nullptr; ctx->sub = nullptr; ctx->gather_buf = nullptr; ctx->slab_buf = nullptr;
+  ctx->borrowed_stream = shared_stream != nullptr;
   {
     const char* e = getenv("MADGPU_FAST_MIN_NX");  // test hook: 0 forces the streaming kernels on every 3-D level
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
@@ -899,7 +1142,8 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
     }                                                                                                          \
   } while (0)
   CUB(cudaSetDevice(p->device));
-  CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  if (shared_stream) ctx->stream = shared_stream;
+  else CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUB(cudaEventCreate(&ctx->ev_a));
   CUB(cudaEventCreate(&ctx->ev_b));
   CUB(cudaEventCreate(&ctx->ev_c));
@@ -907,6 +1151,22 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   int sizes[MADGPU_MAX_LEVELS][3], cent[MADGPU_MAX_LEVELS][3];
   ctx->nlevels = level_schedule(p->dim, p->size, sizes, cent);
   if (ctx->nlevels < 1) { fail(ctx, MADGPU_EINVAL, "too many levels"); return bail(MADGPU_EINVAL); }
+  ctx->total_levels = ctx->nlevels;
+  memcpy(ctx->gsize, sizes, sizeof sizes);
+  memcpy(ctx->gcent, cent, sizeof cent);
+  int La = -1;
+  if (world > 1) {
+    std::string why;
+    La = plan_slabs(ctx->nlevels, sizes, world, why);
+    if (La < 1) { fail(ctx, MADGPU_EINVAL, "cannot cut %dx%dx%d into %d z-slabs: %s", p->size[0], p->size[1], p->size[2], world, why.c_str()); return bail(MADGPU_EINVAL); }
+    const char* ne = nccl_load();
+    if (ne) { fail(ctx, MADGPU_ECUDA, "%s", ne); return bail(MADGPU_ECUDA); }
+    Nccl::UniqueId id;
+    memcpy(&id, nccl_id, sizeof id);
+    const int r = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+    if (r != 0) { fail(ctx, MADGPU_ECUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); ctx->comm = nullptr; return bail(MADGPU_ECUDA); }
+    ctx->nlevels = La + 1;  // this context: the distributed levels and the agglomeration level
+  }
   size_t max_blocks = 0;
   for (int l = 0; l < ctx->nlevels; ++l) {
     Level& L = ctx->lv[l];
@@ -915,7 +1175,18 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
       L.cent[d] = cent[l][d];
       L.h[d] = d < p->dim ? p->spacing[d] * (double)(1u << l) : 1.0;  // mad/itkGridsHierarchy.hxx:80
     }
+    L.gnz = L.n[2];
+    L.zb = 0;
+    if (world > 1) {  // this rank's slab of the level
+      L.n[2] = L.gnz / world;
+      L.zb = rank * L.n[2];
+    }
     fill_geom(L, p->dim, p->time_step);
+    if (world > 1) {
+      L.g.zlo_phys = rank == 0;
+      L.g.zhi_phys = rank == world - 1;
+      L.g.z0 = L.zb;
+    }
     float** fields[3] = {&L.u, &L.f, &L.tmp};
     for (auto f : fields) {
       int rc = dalloc(ctx, L.allocs, f, L.elems);
@@ -944,6 +1215,23 @@ int madgpu_create(const madgpu_params* p, madgpu_ctx** out)
   CUB(cudaMalloc((void**)&ctx->partials, max_blocks * sizeof(double)));
   CUB(cudaMalloc((void**)&ctx->d_scalar, 8 * sizeof(double)));
   CUB(cudaMallocHost((void**)&ctx->h_scalar, 8 * sizeof(double)));
+  if (world > 1) {
+    // agglomeration level: dense staging of the local slab, and on rank 0 the gathered level plus the serial
+    // sub-hierarchy below it (a context of its own on the same stream)
+    const Level& A = ctx->lv[La];
+    const size_t slab = (size_t)A.n[0] * A.n[1] * A.n[2];
+    CUB(cudaMalloc((void**)&ctx->slab_buf, slab * sizeof(float)));
+    if (rank == 0) {
+      CUB(cudaMalloc((void**)&ctx->gather_buf, slab * world * sizeof(float)));
+      madgpu_params sp = *p;
+      sp.world_size = 1;
+      sp.rank = 0;
+      for (int d = 0; d < 3; ++d) { sp.size[d] = sizes[La][d]; sp.spacing[d] = p->spacing[d] * (double)(1u << La); }
+      const int rc = create_ctx(&sp, nullptr, ctx->stream, &ctx->sub);
+      if (rc) { ctx->err = g_create_error; return bail(rc); }
+      if (ctx->sub->nlevels != ctx->total_levels - La) { fail(ctx, MADGPU_ESTATE, "internal: sub-hierarchy depth mismatch"); return bail(MADGPU_ESTATE); }
+    }
+  }
   CUB(cudaStreamSynchronize(ctx->stream));
 #undef CUB
   *out = ctx;
@@ -967,7 +1255,11 @@ void madgpu_destroy(madgpu_ctx* ctx)
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_c) cudaEventDestroy(ctx->ev_c);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->sub) madgpu_destroy(ctx->sub);
+  if (ctx->gather_buf) cudaFree(ctx->gather_buf);
+  if (ctx->slab_buf) cudaFree(ctx->slab_buf);
+  if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->stream && !ctx->borrowed_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
@@ -980,6 +1272,7 @@ int madgpu_set_solver(madgpu_ctx* ctx, int32_t smoother, double omega, int32_t i
   if (max_cycles < 1 || number_of_steps < 1 || iterations_per_grid < 0) return fail(ctx, MADGPU_EINVAL, "bad iteration counts");
   ctx->p.smoother = smoother; ctx->p.omega = omega; ctx->p.iterations_per_grid = iterations_per_grid; ctx->p.cycle = cycle;
   ctx->p.tolerance = tolerance; ctx->p.max_cycles = max_cycles; ctx->p.number_of_steps = number_of_steps; ctx->p.verbose = verbose;
+  if (ctx->sub) return madgpu_set_solver(ctx->sub, smoother, omega, iterations_per_grid, MADGPU_CYCLE_V, tolerance, max_cycles, number_of_steps, 0);
   return 0;
 }
 
@@ -1183,15 +1476,24 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   return 0;
 }
 
-int madgpu_num_levels(const madgpu_ctx* ctx) { return ctx ? ctx->nlevels : MADGPU_EINVAL; }
+int madgpu_slab(const madgpu_ctx* ctx, int32_t level, int32_t* z_begin, int32_t* z_count, int32_t* global_nz)
+{
+  if (!ctx || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
+  if (z_begin) *z_begin = ctx->lv[level].zb;
+  if (z_count) *z_count = ctx->lv[level].n[2];
+  if (global_nz) *global_nz = ctx->lv[level].gnz;
+  return 0;
+}
+
+int madgpu_num_levels(const madgpu_ctx* ctx) { return ctx ? ctx->total_levels : MADGPU_EINVAL; }
 
 int madgpu_level_info(const madgpu_ctx* ctx, int32_t level, int32_t size[3], double spacing[3], int32_t centering[3])
 {
-  if (!ctx || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
-  for (int d = 0; d < 3; ++d) {
-    if (size) size[d] = ctx->lv[level].n[d];
-    if (spacing) spacing[d] = ctx->lv[level].h[d];
-    if (centering) centering[d] = ctx->lv[level].cent[d];
+  if (!ctx || level < 0 || level >= ctx->total_levels) return MADGPU_EINVAL;
+  for (int d = 0; d < 3; ++d) {  // global extents (a z-slab context reports its own planes through madgpu_slab)
+    if (size) size[d] = ctx->gsize[level][d];
+    if (spacing) spacing[d] = d < ctx->dim ? ctx->p.spacing[d] * (double)(1u << level) : 1.0;
+    if (centering) centering[d] = ctx->gcent[level][d];
   }
   return 0;
 }

@@ -24,16 +24,21 @@ VED_SPACING = (0.3125, 0.3125, 0.5)  # test/test_data/ved_test.mhd ElementSpacin
 
 
 def vessel_phantom(shape, device="cpu", seed=1234, spacing=VED_SPACING, eps=0.01, omega=1.5, sensitivity=10.0,
-                   noise_sigma=20.0, dtype=torch.float32):
-    """Returns (image[nz,ny,nx] float32, tensor planes[6,nz,ny,nx] float32: xx,xy,xz,yy,yz,zz)."""
-    nz, ny, nx = shape
+                   noise_sigma=20.0, dtype=torch.float32, z_range=None):
+    """Returns (image[nz,ny,nx] float32, tensor planes[6,nz,ny,nx] float32: xx,xy,xz,yy,yz,zz).
+    z_range=(z0, z1): only that slab of planes of the `shape` volume (z-slab decomposition; the noise of a slab is drawn
+    from its own stream, the vessels and the tensor are identical to the whole volume's)."""
+    nz_global, ny, nx = shape
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
-    z = torch.arange(nz, device=dev, dtype=torch.float32).view(nz, 1, 1) * spacing[2]
+    z0, z1 = (0, nz_global) if z_range is None else z_range
+    gen.manual_seed(seed if z_range is None else seed + 7919 * (z0 + 1))
+    nz = z1 - z0
+    shape = (nz, ny, nx)
+    z = torch.arange(z0, z1, device=dev, dtype=torch.float32).view(nz, 1, 1) * spacing[2]
     y = torch.arange(ny, device=dev, dtype=torch.float32).view(1, ny, 1) * spacing[1]
     x = torch.arange(nx, device=dev, dtype=torch.float32).view(1, 1, nx) * spacing[0]
-    Lx, Ly, Lz = nx * spacing[0], ny * spacing[1], nz * spacing[2]
+    Lx, Ly, Lz = nx * spacing[0], ny * spacing[1], nz_global * spacing[2]
     cx, cy = 0.5 * Lx, 0.5 * Ly
     R = 0.25 * min(Lx, Ly)
     turns = 2.0

@@ -31,10 +31,14 @@ class MadSolver:
 
     def __init__(self, shape, spacing_xyz=None, time_step=0.01, smoother=B.SMOOTHER_GS, omega=2.0 / 3.0,
                  iterations_per_grid=2, cycle=B.CYCLE_V, tolerance=1e-6, max_cycles=100, number_of_steps=1,
-                 verbose=False, gs_colors=4, device=0):
+                 verbose=False, gs_colors=4, device=0, rank=0, world_size=1, nccl_id=None):
+        """shape: the (global) image shape (nz, ny, nx) / (ny, nx).  rank / world_size / nccl_id: this context owns one
+        z-slab of the volume (madgpu_create_slab; see slabs.py); images and tensors passed to it are the local slab."""
         self._lib = B.load()
         self._ctx = C.c_void_p()
-        self.shape = tuple(int(s) for s in shape)
+        self.global_shape = tuple(int(s) for s in shape)
+        self.shape = self.global_shape
+        self.rank, self.world_size = int(rank), int(world_size)
         self.dim = len(self.shape)
         if self.dim not in (2, 3):
             raise MadGpuError("images must be 2-D or 3-D")
@@ -58,8 +62,15 @@ class MadSolver:
         p.verbose = int(bool(verbose))
         p.gs_colors = int(gs_colors)
         p.device = int(device)
+        p.rank, p.world_size = self.rank, self.world_size
         self.params = p
-        rc = self._lib.madgpu_create(C.byref(p), C.byref(self._ctx))
+        if self.world_size > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise MadGpuError("world_size > 1 needs the 128-byte NCCL unique id (slabs.create_unique_id)")
+            self._nccl_id = C.create_string_buffer(bytes(nccl_id), 128)
+            rc = self._lib.madgpu_create_slab(C.byref(p), self._nccl_id, C.byref(self._ctx))
+        else:
+            rc = self._lib.madgpu_create(C.byref(p), C.byref(self._ctx))
         if rc != 0:
             msg = self._lib.madgpu_last_error(None)
             self._ctx = C.c_void_p()
@@ -71,6 +82,13 @@ class MadSolver:
             self._lib.madgpu_level_info(self._ctx, l, n, h, c)
             self.levels.append(dict(n=tuple(n)[: self.dim], h=tuple(h)[: self.dim], centering=tuple(c)[: self.dim],
                                     shape=tuple(n)[: self.dim][::-1]))
+        if self.world_size > 1:
+            zb, zc, gz = C.c_int32(), C.c_int32(), C.c_int32()
+            self._check(self._lib.madgpu_slab(self._ctx, 0, C.byref(zb), C.byref(zc), C.byref(gz)), "slab")
+            self.z_begin, self.z_count = zb.value, zc.value
+            self.shape = (zc.value,) + self.global_shape[1:]
+        else:
+            self.z_begin, self.z_count = 0, self.global_shape[0] if self.dim == 3 else 1
         self.ncomp = 3 if self.dim == 2 else 6
         self.ns = 9 if self.dim == 2 else 27
         self.last_stats = None
