@@ -34,10 +34,10 @@ def launches(path):
     rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[h]
-    kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    kn, mv, mu, mn = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Metric Name")
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows[h + 1:]:
-        if len(r) <= mv:
+        if len(r) <= mv or r[mn] != "gpu__time_duration.sum":
             continue
         v = float(r[mv].replace(",", ""))
         u = r[mu]
