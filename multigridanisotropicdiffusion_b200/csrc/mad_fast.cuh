@@ -19,6 +19,8 @@
 //   k_fast_sweep<MODE_RES>  mad/itkMultigridGaussSeidelSmoother.hxx:114-180 (+ L2Norm partial sums,
 //                           itkMultigridAnisotropicDiffusionImageFilter.hxx:496-515)
 #pragma once
+#include <cuda_fp16.h>
+
 #include "mad_kernels.cuh"
 
 namespace mad {
@@ -428,7 +430,13 @@ __device__ __forceinline__ StepRaw<UT, FT> issue_step(const Geom& g, const Tenso
   return R;
 }
 
-enum { MODE_WJ = 0, MODE_RES = 1 };
+enum { MODE_WJ = 0, MODE_RES = 1, MODE_COEF = 2 };
+
+// Packed operator rows for the Gauss-Seidel smoother: per group of four x-voxels ten fp16 values per voxel, 80 bytes =
+// five 16-byte words; word i holds entries 2i and 2i+1, each for the four voxels.  Entries: 0 1/diag, then the
+// off-diagonal coefficients DIVIDED by diag: 1 x+, 2 x-, 3 y+, 4 y-, 5 z+, 6 z-, 7 xy edges, 8 xz edges, 9 yz edges.
+constexpr int COEF_WORDS = 5;
+__device__ __forceinline__ size_t coef_quad(const Geom& g, int x4, int y, int z) { return ((size_t)z * g.ny + y) * (size_t)(g.pitch >> 2) + x4; }
 
 // One pass over the volume.  MODE_WJ: out = weighted-Jacobi update of u.  MODE_RES: out = f - A u
 // (out may be null) and per-CTA partial sums of its squares (partials may be null).
@@ -475,9 +483,9 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
       if (PF && z + 1 < z1) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z + 1);
       Coef<T> c;
       coefficients<T>(g, D, p, z, oc, S, F, c);
-      float res[4];
+      float res[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4 && MODE != MODE_COEF; ++j) {
         const T s = offdiag<T>(c, um, uc, up, j);
         const T uj = uc.r[1].v[j + 1];
         if (MODE == MODE_WJ) {
@@ -489,7 +497,32 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
           if (p.xt + j < g.nx) sq += (double)r * (double)r;
         }
       }
-      if (out && p.xt < g.nx) store4<OT>(out, oc, p.xt, g.nx, res);
+      if (MODE != MODE_COEF && out && p.xt < g.nx) store4<OT>(out, oc, p.xt, g.nx, res);
+      if (MODE == MODE_COEF && p.xt < g.nx) {
+        __half2 h[10][2];
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const float i0 = 1.f / float(c.diag[j]), i1 = 1.f / float(c.diag[j + 1]);
+          h[0][j >> 1] = __floats2half2_rn(i0, i1);
+          h[1][j >> 1] = __floats2half2_rn(float(c.xp[j]) * i0, float(c.xp[j + 1]) * i1);
+          h[2][j >> 1] = __floats2half2_rn(float(c.xm[j]) * i0, float(c.xm[j + 1]) * i1);
+          h[3][j >> 1] = __floats2half2_rn(float(c.yp[j]) * i0, float(c.yp[j + 1]) * i1);
+          h[4][j >> 1] = __floats2half2_rn(float(c.ym[j]) * i0, float(c.ym[j + 1]) * i1);
+          h[5][j >> 1] = __floats2half2_rn(float(c.zp[j]) * i0, float(c.zp[j + 1]) * i1);
+          h[6][j >> 1] = __floats2half2_rn(float(c.zm[j]) * i0, float(c.zm[j + 1]) * i1);
+          h[7][j >> 1] = __floats2half2_rn(float(c.exy[j]) * i0, float(c.exy[j + 1]) * i1);
+          h[8][j >> 1] = __floats2half2_rn(float(c.exz[j]) * i0, float(c.exz[j + 1]) * i1);
+          h[9][j >> 1] = __floats2half2_rn(float(c.eyz[j]) * i0, float(c.eyz[j + 1]) * i1);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out) + coef_quad(g, p.xt >> 2, p.y, z) * COEF_WORDS;
+#pragma unroll
+        for (int i = 0; i < COEF_WORDS; ++i) {
+          uint4 q;
+          q.x = *reinterpret_cast<unsigned*>(&h[2 * i][0]); q.y = *reinterpret_cast<unsigned*>(&h[2 * i][1]);
+          q.z = *reinterpret_cast<unsigned*>(&h[2 * i + 1][0]); q.w = *reinterpret_cast<unsigned*>(&h[2 * i + 1][1]);
+          dst[i] = q;
+        }
+      }
       um = uc; uc = up;
       S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
       S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
@@ -517,7 +550,10 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 // New values travel: own row -> registers; x-neighbours -> warp shuffles; rows y+-1 of the plane
 // being updated and of the plane below -> shared memory (two row buffers, alternating with z).
 // ------------------------------------------------------------------------------------------
-template <int WY, int MINB, bool PF>
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int WY, int MINB, bool PF, bool SPLIT>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, const float* __restrict__ u, const float* __restrict__ f,
                                                              float* __restrict__ out, int zc, int pfd)
 {
@@ -559,18 +595,177 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
     if (PF && z + 1 < z1) R = issue_step<float, float>(g, D, u, f, p, rowo, z + 1);
     Coef<float> c;
     coefficients<float>(g, D, p, z, oc, S, F, c);
-    // plane z-1 was updated one step ago: rows y+-1 come from the tile's row buffer (own row: registers)
+    // rows y+-1 of the plane below (updated one step ago) and, for odd rows, of this plane (updated in this step's
+    // first phase) come from the tile's row buffers
+    auto rows_below = [&]() {
+      if (has_m) { const float4 q = sh[pb][wm][p.lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
+      if (has_p) { const float4 q = sh[pb][wp][p.lane]; um.r[2].v[1] = q.x; um.r[2].v[2] = q.y; um.r[2].v[3] = q.z; um.r[2].v[4] = q.w; }
+    };
+    auto even_rows_of_this_plane = [&]() {
+      const float* sm = reinterpret_cast<const float*>(&sh[cb][has_m ? wm : 0][0]);
+      const float* sp = reinterpret_cast<const float*>(&sh[cb][has_p ? wp : 0][0]);
+      if (has_m) {
+        const float4 q = reinterpret_cast<const float4*>(sm)[p.lane];
+        uc.r[0].v[1] = q.x; uc.r[0].v[2] = q.y; uc.r[0].v[3] = q.z; uc.r[0].v[4] = q.w;
+        if (p.lane > 0) uc.r[0].v[0] = sm[p.lane * 4 - 1];
+        if (p.lane < 31) uc.r[0].v[5] = sm[p.lane * 4 + 4];
+      }
+      if (has_p) {
+        const float4 q = reinterpret_cast<const float4*>(sp)[p.lane];
+        uc.r[2].v[1] = q.x; uc.r[2].v[2] = q.y; uc.r[2].v[3] = q.z; uc.r[2].v[4] = q.w;
+        if (p.lane > 0) uc.r[2].v[0] = sp[p.lane * 4 - 1];
+        if (p.lane < 31) uc.r[2].v[5] = sp[p.lane * 4 + 4];
+      }
+      if (p.xb) { mirror_x(uc.r[0], p.xt, p.jl); mirror_x(uc.r[2], p.xt, p.jl); }
+    };
+    auto update_row = [&]() {
+      // even x (slots 0, 2): x-neighbours still hold the values of the previous sweep
+      const float n0 = fast_div(fv.v[0] - offdiag<float>(c, um, uc, up, 0), c.diag[0]);  // mad/itkMultigridGaussSeidelSmoother.hxx:99
+      const float n2 = fast_div(fv.v[2] - offdiag<float>(c, um, uc, up, 2), c.diag[2]);
+      uc.r[1].v[1] = n0; uc.r[1].v[3] = n2;
+      {
+        const float r = __shfl_down_sync(FULL, n0, 1);
+        if (p.lane < 31) uc.r[1].v[5] = r;
+        if (p.xb) mirror_x(uc.r[1], p.xt, p.jl);
+      }
+      // odd x (slots 1, 3)
+      const float n1 = fast_div(fv.v[1] - offdiag<float>(c, um, uc, up, 1), c.diag[1]);
+      const float n3 = fast_div(fv.v[3] - offdiag<float>(c, um, uc, up, 3), c.diag[3]);
+      uc.r[1].v[2] = n1; uc.r[1].v[4] = n3;
+      {
+        const float l = __shfl_up_sync(FULL, n3, 1);
+        if (p.lane > 0) uc.r[1].v[0] = l;
+        if (p.xb) mirror_x(uc.r[1], p.xt, p.jl);
+      }
+      sh[cb][w][p.lane] = make_float4(n0, n1, n2, n3);
+      const float res[4] = {n0, n1, n2, n3};
+      if (p.xt < g.nx) store4<float>(out, oc, p.xt, g.nx, res);
+    };
+    const bool last_plane = z == g.nz - 1 && g.zhi_phys;  // the mirrored plane z+1 IS plane z-1, which has already been updated
+    if (SPLIT) {
+      // Producer/consumer barriers instead of CTA-wide ones: barrier 2 = "even rows of this plane published" (even-row
+      // warps arrive, odd-row warps wait), barrier 1 = "odd rows published" (the other way round).  A warp that has
+      // published runs ahead into the loads and the coefficient arithmetic of the next plane, which depend on no other
+      // warp, while the other parity relaxes its rows.
+      constexpr int NT = 32 * WY;
+      const bool even = (w & 1) == 0;
+      if (even) {
+        if (z > z0) { bar_sync(1, NT); rows_below(); }
+      } else {
+        // (the even rows of the plane below are already in registers: read from the row buffer one step ago)
+        bar_sync(2, NT);
+        if (valid) even_rows_of_this_plane();
+      }
+      if (last_plane) up = um;
+      if (valid) update_row();
+      __threadfence_block();
+      if (even) bar_arrive(2, NT);
+      else bar_arrive(1, NT);
+    } else {
+      if (z > z0) rows_below();
+      if (last_plane) up = um;
+#pragma unroll 1
+      for (int phase = 0; phase < 2; ++phase) {
+        if (valid && (w & 1) == phase) {
+          if (phase == 1) even_rows_of_this_plane();
+          update_row();
+        }
+        __syncthreads();
+      }
+    }
+    um = uc; uc = up;
+    S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
+    S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
+  }
+}
+
+// The same fused Gauss-Seidel sweep fed by PRE-EVALUATED operator rows (k_fast_sweep<MODE_COEF>): ten fp16 values per
+// voxel (20 B) instead of the six fp32 tensor planes (24 B) and ~2/3 of the instructions (no tensor differences, no tensor
+// halo traffic).  fp16 rows make this a Gauss-Seidel sweep on an operator rounded to 11 bits -- a smoother just as good, and
+// harmless to the result: every cycle is a correction to the fp64 defect f - A u evaluated with the exact rows, so the
+// fixed point is the reference's (Gauss-Seidel parity is stated on the converged image).  Weighted Jacobi, whose parity is
+// stated per V-cycle, keeps the exact on-the-fly rows.
+struct CoefRaw {
+  uint4 w[COEF_WORDS];
+};
+__device__ __forceinline__ CoefRaw issue_coef(const uint4* __restrict__ coef, const Geom& g, const Pos& p, int y, int z)
+{
+  CoefRaw r;
+  const uint4* src = coef + coef_quad(g, p.xl >> 2, y, z) * COEF_WORDS;
+#pragma unroll
+  for (int i = 0; i < COEF_WORDS; ++i) r.w[i] = __ldg(src + i);
+  return r;
+}
+// entry k (0..9) of voxel j (0..3)
+__device__ __forceinline__ float coef_at(const CoefRaw& r, int k, int j)
+{
+  const uint4& q = r.w[k >> 1];
+  const unsigned u = (k & 1) ? (j < 2 ? q.z : q.w) : (j < 2 ? q.x : q.y);
+  const __half2 h = *reinterpret_cast<const __half2*>(&u);
+  return (j & 1) ? __high2float(h) : __low2float(h);
+}
+// normalised off-diagonal sum at slot j
+__device__ __forceinline__ float offdiag16(const CoefRaw& c, const UPlane<float>& m, const UPlane<float>& q, const UPlane<float>& n, int j)
+{
+  float s = coef_at(c, 1, j) * q.r[1].v[j + 2] + coef_at(c, 2, j) * q.r[1].v[j] + coef_at(c, 3, j) * q.r[2].v[j + 1] + coef_at(c, 4, j) * q.r[0].v[j + 1];
+  s += coef_at(c, 7, j) * ((q.r[2].v[j + 2] - q.r[0].v[j + 2]) - (q.r[2].v[j] - q.r[0].v[j]));
+  s += coef_at(c, 5, j) * n.r[1].v[j + 1] + coef_at(c, 6, j) * m.r[1].v[j + 1];
+  s += coef_at(c, 8, j) * ((n.r[1].v[j + 2] - m.r[1].v[j + 2]) - (n.r[1].v[j] - m.r[1].v[j]));
+  s += coef_at(c, 9, j) * ((n.r[2].v[j + 1] - m.r[2].v[j + 1]) - (n.r[0].v[j + 1] - m.r[0].v[j + 1]));
+  return s;
+}
+
+// L2 prefetch of one plane step of this kernel: u (4 lines), f (4 lines), packed rows (20 lines) of the warp's row
+__device__ __forceinline__ const char* coef_prefetch_base(const Geom& g, const float* u, const float* f, const uint4* coef, int lane, int y)
+{
+  const size_t x0 = (size_t)blockIdx.x * TX;
+  if (lane < 4) return reinterpret_cast<const char*>(u + (size_t)y * g.pitch + x0) + lane * 128;
+  if (lane < 8) return reinterpret_cast<const char*>(f + (size_t)y * g.pitch + x0) + (lane - 4) * 128;
+  if (lane < 28) return reinterpret_cast<const char*>(coef + ((size_t)y * (g.pitch >> 2) + (x0 >> 2)) * COEF_WORDS) + (lane - 8) * 128;
+  return nullptr;
+}
+
+template <int WY, int MINB>
+__global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
+                                                             const float* __restrict__ f, float* __restrict__ out, int zc, int pfd)
+{
+  static_assert(WY % 2 == 0, "row colours alternate with the warp index");
+  __shared__ float4 sh[2][WY][32];
+  const Pos p = make_pos(g);
+  const int w = threadIdx.y;
+  const bool valid = p.y < g.ny;
+  const int y = valid ? p.y : 0;
+  const int wm = p.ylo ? w + 1 : w - 1, wp = p.yhi ? w - 1 : w + 1;
+  const bool has_m = wm >= 0 && wm < WY, has_p = wp >= 0 && wp < WY && blockIdx.y * WY + wp < g.ny;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
+  const int rowo = y * g.pitch + p.xl;
+  const char* pf = coef_prefetch_base(g, u, f, coef, p.lane, y);
+  const long long pf_stride = p.lane < 8 ? g.plane * 4ll : (long long)g.ny * (g.pitch >> 2) * COEF_WORDS * 16ll;
+  const int zpf_end = min(z1 + 1, g.nz);
+  UPlane<float> um, uc, up;
+  {
+    const URaw<float> r0 = issue_u(u, zmirror_lo(g, z0) * (int)g.plane + rowo, p), r1 = issue_u(u, z0 * (int)g.plane + rowo, p);
+    finish_u<float, float>(r0, p, um);
+    finish_u<float, float>(r1, p, uc);
+  }
+  for (int z = z0; z < z1; ++z) {
+    const int oc = z * (int)g.plane + rowo;
+    const int cb = z & 1, pb = cb ^ 1;
+    if (pfd > 0 && z + pfd < zpf_end && pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + pf_stride * (z + pfd)));
+    const URaw<float> ru = issue_u(u, zmirror_hi(g, z) * (int)g.plane + rowo, p);
+    const CoefRaw c = issue_coef(coef, g, p, y, z);
+    const Raw4<float> rf = issue4(f, oc);
+    finish_u<float, float>(ru, p, up);
+    const V4<float> fv = finish4<float>(rf);
     if (z > z0) {
       if (has_m) { const float4 q = sh[pb][wm][p.lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
       if (has_p) { const float4 q = sh[pb][wp][p.lane]; um.r[2].v[1] = q.x; um.r[2].v[2] = q.y; um.r[2].v[3] = q.z; um.r[2].v[4] = q.w; }
     }
-    // last plane of the image: the mirrored plane z+1 IS plane z-1, which has already been updated
     if (z == g.nz - 1 && g.zhi_phys) up = um;
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
       if (valid && (w & 1) == phase) {
         if (phase == 1) {
-          // odd row: rows y+-1 of this plane are even rows, updated in phase 0
           const float* sm = reinterpret_cast<const float*>(&sh[cb][has_m ? wm : 0][0]);
           const float* sp = reinterpret_cast<const float*>(&sh[cb][has_p ? wp : 0][0]);
           if (has_m) {
@@ -587,18 +782,16 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
           }
           if (p.xb) { mirror_x(uc.r[0], p.xt, p.jl); mirror_x(uc.r[2], p.xt, p.jl); }
         }
-        // even x (slots 0, 2): x-neighbours still hold the values of the previous sweep
-        const float n0 = fast_div(fv.v[0] - offdiag<float>(c, um, uc, up, 0), c.diag[0]);  // mad/itkMultigridGaussSeidelSmoother.hxx:99
-        const float n2 = fast_div(fv.v[2] - offdiag<float>(c, um, uc, up, 2), c.diag[2]);
+        const float n0 = fv.v[0] * coef_at(c, 0, 0) - offdiag16(c, um, uc, up, 0);
+        const float n2 = fv.v[2] * coef_at(c, 0, 2) - offdiag16(c, um, uc, up, 2);
         uc.r[1].v[1] = n0; uc.r[1].v[3] = n2;
         {
           const float r = __shfl_down_sync(FULL, n0, 1);
           if (p.lane < 31) uc.r[1].v[5] = r;
           if (p.xb) mirror_x(uc.r[1], p.xt, p.jl);
         }
-        // odd x (slots 1, 3)
-        const float n1 = fast_div(fv.v[1] - offdiag<float>(c, um, uc, up, 1), c.diag[1]);
-        const float n3 = fast_div(fv.v[3] - offdiag<float>(c, um, uc, up, 3), c.diag[3]);
+        const float n1 = fv.v[1] * coef_at(c, 0, 1) - offdiag16(c, um, uc, up, 1);
+        const float n3 = fv.v[3] * coef_at(c, 0, 3) - offdiag16(c, um, uc, up, 3);
         uc.r[1].v[2] = n1; uc.r[1].v[4] = n3;
         {
           const float l = __shfl_up_sync(FULL, n3, 1);
@@ -612,8 +805,6 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
       __syncthreads();
     }
     um = uc; uc = up;
-    S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
-    S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
   }
 }
 

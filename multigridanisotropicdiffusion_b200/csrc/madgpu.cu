@@ -44,6 +44,8 @@ struct Level {
   size_t elems;  // allocation size in elements (incl. 2 ghost planes)
   float *u, *f, *tmp;  // plane-0 pointers
   float* D[6];
+  uint4* coef16;      // packed fp16 operator rows for the Gauss-Seidel smoother (mad_fast.cuh), built on first use
+  bool coef16_valid;
   std::vector<void*> allocs;
 };
 
@@ -109,6 +111,7 @@ struct madgpu_ctx {
   int total_levels;    // levels of the whole hierarchy (distributed + serial)
   int gsize[MADGPU_MAX_LEVELS][3], gcent[MADGPU_MAX_LEVELS][3];  // global level schedule
   int pf_dist;      // L2 prefetch distance (planes) of the streaming kernels, 0 = off
+  int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
@@ -396,24 +399,50 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
       else if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       else k_jacobi<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       std::swap(L.u, L.tmp);
+    } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16) {
+      // fused sweep fed by pre-evaluated fp16 operator rows (built once per tensor and level)
+      if (!L.coef16_valid) {
+        if (!L.coef16) {
+          void* q = nullptr;
+          const size_t bytes = (size_t)L.g.nz * L.g.ny * (size_t)(L.g.pitch >> 2) * fast::COEF_WORDS * sizeof(uint4);
+          if (cudaMalloc(&q, bytes) != cudaSuccess) { latch(ctx, 0, ""); ctx->sticky = "out of device memory for the packed Gauss-Seidel rows"; cudaGetLastError(); return; }
+          L.allocs.push_back(q);
+          L.coef16 = (uint4*)q;
+        }
+        Scope sb(ctx, MADGPU_K_MISC);
+        launch_fast<fast::MODE_COEF, float, float, float, float>(ctx, L, L.u, L.f, reinterpret_cast<float*>(L.coef16), nullptr, 0.f);
+        L.coef16_valid = true;
+      }
+      Scope s(ctx, cls);
+      {
+        const int zc = fast_zc(L.g, 4);
+        fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+      }
+      std::swap(L.u, L.tmp);
     } else if (use_fast(ctx, L) && ctx->gs_fused) {
       // one pass: z-ordered planes, four in-plane colours, exact inside a CTA tile (mad_fast.cuh)
       Scope s(ctx, cls);
       if (ctx->fast_cfg == 1) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<8, 1, false, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       } else if (ctx->fast_cfg == 4) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 2, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<4, 2, true, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       } else if (ctx->fast_cfg == 5) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<8, 1, true, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+      } else if (ctx->fast_cfg == 7) {
+        const int zc = fast_zc(L.g, 4);
+        fast::k_fast_gs<4, 3, false, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+      } else if (ctx->fast_cfg == 8) {
+        const int zc = fast_zc(L.g, 8);
+        fast::k_fast_gs<8, 1, false, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       } else if (ctx->fast_cfg == 6) {
         const int zc = fast_zc(L.g, 2);
-        fast::k_fast_gs<2, 6, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<2, 6, false, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<4, 3, false, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
       }
       std::swap(L.u, L.tmp);
     } else {
@@ -843,6 +872,7 @@ int build_coarse_solver(madgpu_ctx* ctx)
 // After level-0 tensor planes are filled: restrict them down the hierarchy and build the coarse solver.
 int finish_tensor(madgpu_ctx* ctx)
 {
+  for (int l = 0; l < ctx->nlevels; ++l) ctx->lv[l].coef16_valid = false;
   for (int l = 0; l + 1 < ctx->nlevels; ++l)
     for (int c = 0; c < ctx->ncomp; ++c)  // mad/itkGridsHierarchy.hxx:149-162
       op_restrict<float>(ctx, l, ctx->lv[l].D[c], ctx->lv[l + 1].D[c], MADGPU_K_MISC);
@@ -1125,6 +1155,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
     e = getenv("MADGPU_PF_DIST");
     ctx->pf_dist = e ? atoi(e) : 2;
+    e = getenv("MADGPU_GS_COEF16");
+    ctx->gs_coef16 = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_FUSED");
     ctx->gs_fused = e ? atoi(e) : 1;
     e = getenv("MADGPU_FAST_CFG");
@@ -1193,6 +1225,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
       if (rc) return bail(rc);
       *f += L.g.plane;
     }
+    L.coef16 = nullptr;
+    L.coef16_valid = false;
     for (int c = 0; c < 6; ++c) L.D[c] = nullptr;
     for (int c = 0; c < ctx->ncomp; ++c) {
       int rc = dalloc(ctx, L.allocs, &L.D[c], L.elems);
@@ -1468,7 +1502,7 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (!ctx || !tile || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
   const Level& L = ctx->lv[level];
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
-    const int wy = (ctx->fast_cfg == 1 || ctx->fast_cfg == 5) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
+    const int wy = ctx->gs_coef16 ? 4 : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
     tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level

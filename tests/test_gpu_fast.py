@@ -137,10 +137,12 @@ GS_CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1], ids=lambda c: f"cfg{c}")
+@pytest.fixture(params=[(0, 0), (1, 0), (7, 0), (8, 0), (0, 1)], ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}")
 def gs_env(request, monkeypatch):
+    """(kernel variant, packed fp16 operator rows): the default is (0, 1); the exact-row variants pin the ordering."""
     monkeypatch.setenv("MADGPU_FAST_MIN_NX", "0")
-    monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param))
+    monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param[0]))
+    monkeypatch.setenv("MADGPU_GS_COEF16", str(request.param[1]))
     return request.param
 
 
@@ -155,13 +157,16 @@ def test_fused_gs_sweep_is_the_documented_ordering(case, gs_env):
     shape = case[0]
     u, f = random_image(shape, seed=1), random_image(shape, seed=2)
     S = o.stencil(0)
+    # exact rows: fp32 rounding only; packed fp16 rows: the operator itself is rounded to 11 bits (the smoother inside
+    # an exact defect-correction loop, see k_coef_gs)
+    tol = 2e-6 if gs_env[1] == 0 else 2e-3
     g1 = s.op_smooth(0, u, f, smoother=0, n_iter=1)
     r1 = gs_tile_sweep(S, u.astype(np.float64), f.astype(np.float64), tile)
-    assert rel_l2(g1, r1) < 2e-6, rel_l2(g1, r1)
-    assert np.abs(g1 - r1).max() < 3e-5 * np.abs(r1).max()
+    assert rel_l2(g1, r1) < tol, rel_l2(g1, r1)
+    assert np.abs(g1 - r1).max() < 15 * tol * np.abs(r1).max()
     g2 = s.op_smooth(0, u, f, smoother=0, n_iter=2)
     r2 = gs_tile_sweep(S, r1, f.astype(np.float64), tile)
-    assert rel_l2(g2, r2) < 4e-6, rel_l2(g2, r2)
+    assert rel_l2(g2, r2) < 2 * tol, rel_l2(g2, r2)
     s.close()
 
 
