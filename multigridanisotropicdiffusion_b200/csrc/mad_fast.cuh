@@ -394,6 +394,15 @@ __device__ __forceinline__ void finish_u(const URaw<UT>& R, const Pos& p, UPlane
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void zero_uplane(UPlane<T>& P)
+{
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) P.r[i].v[k] = T(0);
+}
+
 // sum over the off-diagonal entries at slot j (apply_offdiag of mad_kernels.cuh on registers)
 template <typename T>
 __device__ __forceinline__ T offdiag(const Coef<T>& c, const UPlane<T>& m, const UPlane<T>& q, const UPlane<T>& n, int j)
@@ -445,8 +454,9 @@ __device__ __forceinline__ size_t coef_quad(const Geom& g, int x4, int y, int z)
 // registers) instead of at the top of step z+1.
 template <int MODE, typename T, typename UT, typename FT, typename OT, int WY, int MINB, bool PF>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, const UT* __restrict__ u, const FT* __restrict__ f,
-                                                         OT* __restrict__ out, double* __restrict__ partials, float omega, int zc, int pfd)
+                                                         OT* __restrict__ out, double* __restrict__ partials, float omega, int zc, int pfd, int uzero)
 {
+  // uzero: the iterate is identically zero (first sweep of a V-cycle leg): `u` is not read
   const Pos p = make_pos(g);
   const bool valid = p.y < g.ny;
   double sq = 0.0;
@@ -460,10 +470,13 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
     DzState S;
     {
       const int o_m = zmirror_lo(g, z0) * (int)g.plane + rowo, o_c = z0 * (int)g.plane + rowo;
-      const URaw<UT> r0 = issue_u(u, o_m, p), r1 = issue_u(u, o_c, p);
       const DzRaw d0 = issue_dz(D, o_m, p), d1 = issue_dz(D, o_c, p);
-      finish_u<T, UT>(r0, p, um);
-      finish_u<T, UT>(r1, p, uc);
+      if (uzero) { zero_uplane(um); zero_uplane(uc); }
+      else {
+        const URaw<UT> r0 = issue_u(u, o_m, p), r1 = issue_u(u, o_c, p);
+        finish_u<T, UT>(r0, p, um);
+        finish_u<T, UT>(r1, p, uc);
+      }
       S.xz_m = finish4<float>(d0.xz.c); S.yz_m = finish4<float>(d0.yz); S.zz_m = finish4<float>(d0.zz);
       S.xz_c = finish6<float, float>(d1.xz, p); S.yz_c = finish4<float>(d1.yz); S.zz_c = finish4<float>(d1.zz);
     }
@@ -476,6 +489,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
       if (!PF) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z);
       // ---- consume the loads issued one step ago ----
       finish_u<T, UT>(R.u, p, up);
+      if (uzero) zero_uplane(up);
       S.xz_p = finish6<float, float>(R.dz.xz, p); S.yz_p = finish4<float>(R.dz.yz); S.zz_p = finish4<float>(R.dz.zz);
       const DcFin F = finish_dc(R.dc, p);
       const V4<T> fv = finish4<T>(R.f);
@@ -555,7 +569,7 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile(
 
 template <int WY, int MINB, bool PF, bool SPLIT>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, const float* __restrict__ u, const float* __restrict__ f,
-                                                             float* __restrict__ out, int zc, int pfd)
+                                                             float* __restrict__ out, int zc, int pfd, int uzero)
 {
   static_assert(WY % 2 == 0, "row colours alternate with the warp index");
   __shared__ float4 sh[2][WY][32];
@@ -572,10 +586,13 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
   DzState S;
   {
     const int o_m = zmirror_lo(g, z0) * (int)g.plane + rowo, o_c = z0 * (int)g.plane + rowo;
-    const URaw<float> r0 = issue_u(u, o_m, p), r1 = issue_u(u, o_c, p);
     const DzRaw d0 = issue_dz(D, o_m, p), d1 = issue_dz(D, o_c, p);
-    finish_u<float, float>(r0, p, um);
-    finish_u<float, float>(r1, p, uc);
+    if (uzero) { zero_uplane(um); zero_uplane(uc); }
+    else {
+      const URaw<float> r0 = issue_u(u, o_m, p), r1 = issue_u(u, o_c, p);
+      finish_u<float, float>(r0, p, um);
+      finish_u<float, float>(r1, p, uc);
+    }
     S.xz_m = finish4<float>(d0.xz.c); S.yz_m = finish4<float>(d0.yz); S.zz_m = finish4<float>(d0.zz);
     S.xz_c = finish6<float, float>(d1.xz, p); S.yz_c = finish4<float>(d1.yz); S.zz_c = finish4<float>(d1.zz);
   }
@@ -588,6 +605,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
     if (pfd > 0 && z + pfd < zpf_end) prefetch_plane(PFL, z + pfd);
     if (!PF) R = issue_step<float, float>(g, D, u, f, p, rowo, z);
     finish_u<float, float>(R.u, p, up);
+    if (uzero) zero_uplane(up);
     S.xz_p = finish6<float, float>(R.dz.xz, p); S.yz_p = finish4<float>(R.dz.yz); S.zz_p = finish4<float>(R.dz.zz);
     const DcFin F = finish_dc(R.dc, p);
     const V4<float> fv = finish4<float>(R.f);
@@ -727,7 +745,7 @@ __device__ __forceinline__ const char* coef_prefetch_base(const Geom& g, const f
 
 template <int WY, int MINB>
 __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
-                                                             const float* __restrict__ f, float* __restrict__ out, int zc, int pfd)
+                                                             const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero)
 {
   static_assert(WY % 2 == 0, "row colours alternate with the warp index");
   __shared__ float4 sh[2][WY][32];
@@ -743,7 +761,8 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
   const long long pf_stride = p.lane < 8 ? g.plane * 4ll : (long long)g.ny * (g.pitch >> 2) * COEF_WORDS * 16ll;
   const int zpf_end = min(z1 + 1, g.nz);
   UPlane<float> um, uc, up;
-  {
+  if (uzero) { zero_uplane(um); zero_uplane(uc); }
+  else {
     const URaw<float> r0 = issue_u(u, zmirror_lo(g, z0) * (int)g.plane + rowo, p), r1 = issue_u(u, z0 * (int)g.plane + rowo, p);
     finish_u<float, float>(r0, p, um);
     finish_u<float, float>(r1, p, uc);
@@ -751,11 +770,14 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
   for (int z = z0; z < z1; ++z) {
     const int oc = z * (int)g.plane + rowo;
     const int cb = z & 1, pb = cb ^ 1;
-    if (pfd > 0 && z + pfd < zpf_end && pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + pf_stride * (z + pfd)));
-    const URaw<float> ru = issue_u(u, zmirror_hi(g, z) * (int)g.plane + rowo, p);
+    if (pfd > 0 && z + pfd < zpf_end && pf && !(uzero && p.lane < 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + pf_stride * (z + pfd)));
     const CoefRaw c = issue_coef(coef, g, p, y, z);
     const Raw4<float> rf = issue4(f, oc);
-    finish_u<float, float>(ru, p, up);
+    if (uzero) zero_uplane(up);
+    else {
+      const URaw<float> ru = issue_u(u, zmirror_hi(g, z) * (int)g.plane + rowo, p);
+      finish_u<float, float>(ru, p, up);
+    }
     const V4<float> fv = finish4<float>(rf);
     if (z > z0) {
       if (has_m) { const float4 q = sh[pb][wm][p.lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
@@ -808,6 +830,46 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
   }
 }
 
+// r = f - A u from the packed rows (the residual that feeds the restriction INSIDE a Gauss-Seidel V-cycle: it is taken
+// with the same fp16-rounded operator the sweeps relax, so the inner cycle is a consistent multigrid cycle for that
+// operator; the outer defect and the stop test keep the exact rows).  Same marching structure, no phases.
+template <int WY, int MINB>
+__global__ void __launch_bounds__(32 * WY, MINB) k_coef_residual(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
+                                                                   const float* __restrict__ f, float* __restrict__ out, int zc, int pfd)
+{
+  const Pos p = make_pos(g);
+  if (p.y >= g.ny) return;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
+  const int rowo = p.y * g.pitch + p.xl;
+  const char* pf = coef_prefetch_base(g, u, f, coef, p.lane, p.y);
+  const long long pf_stride = p.lane < 8 ? g.plane * 4ll : (long long)g.ny * (g.pitch >> 2) * COEF_WORDS * 16ll;
+  const int zpf_end = min(z1 + 1, g.nz);
+  UPlane<float> um, uc, up;
+  {
+    const URaw<float> r0 = issue_u(u, zmirror_lo(g, z0) * (int)g.plane + rowo, p), r1 = issue_u(u, z0 * (int)g.plane + rowo, p);
+    finish_u<float, float>(r0, p, um);
+    finish_u<float, float>(r1, p, uc);
+  }
+  for (int z = z0; z < z1; ++z) {
+    const int oc = z * (int)g.plane + rowo;
+    if (pfd > 0 && z + pfd < zpf_end && pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + pf_stride * (z + pfd)));
+    const URaw<float> ru = issue_u(u, zmirror_hi(g, z) * (int)g.plane + rowo, p);
+    const CoefRaw c = issue_coef(coef, g, p, p.y, z);
+    const Raw4<float> rf = issue4(f, oc);
+    finish_u<float, float>(ru, p, up);
+    const V4<float> fv = finish4<float>(rf);
+    float res[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float inv = coef_at(c, 0, j);
+      // rows are stored divided by diag: A u = (u + sum_k c_k u_k) / inv
+      res[j] = __fdividef(fv.v[j] * inv - uc.r[1].v[j + 1] - offdiag16(c, um, uc, up, j), inv);
+    }
+    if (p.xt < g.nx) store4<float>(out, oc, p.xt, g.nx, res);
+    um = uc; uc = up;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Inter-grid transfers, 4 fine voxels per thread along x.
 // ------------------------------------------------------------------------------------------
@@ -816,19 +878,36 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
 // tables .h:101-113) fused with the correction add of the V-cycle (…Filter.hxx:424-435).
 // The four fine voxels 4t..4t+3 of a thread interpolate from the coarse voxels 2t-1..2t+2 of up to four
 // coarse rows: 3 loads per coarse row (one 8-byte pair + two scalars), one 16-byte load/store of the fine row.
-// grid = (ceil(nxf/128), ceil(nyf/WY), nzf), block = (32, WY).
-template <bool ADD, int WY>
-__global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Transfer t, const float* __restrict__ coarse, float* __restrict__ fine)
+constexpr int PROLONG_ZB = 8;  // fine planes per CTA (a CTA per plane would be ~10^5 very short CTAs on a 512^3 level)
+
+// interpolated values of the thread's four fine voxels of row (y, z)
+__device__ __forceinline__ void prolong_row(const Geom& gc, const Geom& gf, const Transfer& t, const float* __restrict__ coarse, int xt, int y, int z,
+                                            float acc[4])
 {
-  const int lane = threadIdx.x;
-  const int xt = blockIdx.x * TX + lane * 4;
-  const int y = blockIdx.y * WY + threadIdx.y;
-  const int z = blockIdx.z;
-  if (xt >= gf.nx || y >= gf.ny) return;
   int y0, y1, z0, z1;
   float wy0, wy1, wz0, wz1;
   prolong_taps(y, gf.ny, gc.ny, t.cent[1], y0, y1, wy0, wy1);
   prolong_taps(z, gf.nz, gc.nz, t.cent[2], z0, z1, wz0, wz1, gf.zlo_phys != 0, gf.zhi_phys != 0);
+  if (t.cent[0] == 1 && xt > 0 && xt + 4 < gf.nx) {
+    // cell-centred axis away from the two ends (every thread but two per row on power-of-two volumes): fixed 3/4, 1/4 taps,
+    // fine 4t..4t+3 from coarse 2t-1..2t+2
+    const int cb = (xt >> 1) - 1;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int yy = (r & 1) ? y1 : y0, zz = (r & 2) ? z1 : z0;
+      const float wr = ((r & 1) ? wy1 : wy0) * ((r & 2) ? wz1 : wz0);
+      const float* row = coarse + (long long)zz * gc.plane + (long long)yy * gc.pitch + cb;
+      const float c0 = __ldg(row), c3 = __ldg(row + 3);
+      const float2 c12 = __ldg(reinterpret_cast<const float2*>(row + 1));
+      a0 += wr * (.75f * c12.x + .25f * c0);
+      a1 += wr * (.75f * c12.x + .25f * c12.y);
+      a2 += wr * (.75f * c12.y + .25f * c12.x);
+      a3 += wr * (.75f * c12.y + .25f * c3);
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3;
+    return;
+  }
   // x taps of the four fine voxels as weights on the coarse voxels cb..cb+3, cb = 2t-1
   const int cb = (xt >> 1) - 1;
   float W[4][4];
@@ -844,7 +923,7 @@ __global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Tran
   const int xa = max(cb, 0), xd = min(cb + 3, gc.nx - 1);            // clamped (their weights are zero when clamped)
   const int xb = cb + 1, xc = min(cb + 2, gc.nx - 1);               // cb+1 = 2t is always a valid, 8-byte aligned voxel
   const bool pair = xb + 1 < gc.nx;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int yy = (r & 1) ? y1 : y0, zz = (r & 2) ? z1 : z0;
@@ -859,12 +938,26 @@ __global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Tran
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] += wr * (W[j][0] * c[0] + W[j][1] * c[1] + W[j][2] * c[2] + W[j][3] * c[3]);
   }
-  const int o = z * (int)gf.plane + y * gf.pitch + xt;
-  if (ADD) {
-    const float4 q = *reinterpret_cast<const float4*>(fine + o);
-    acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+}
+
+// grid = (ceil(nxf/128), ceil(nyf/WY), ceil(nzf/PROLONG_ZB)), block = (32, WY)
+template <bool ADD, int WY>
+__global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Transfer t, const float* __restrict__ coarse, float* __restrict__ fine)
+{
+  const int xt = blockIdx.x * TX + threadIdx.x * 4;
+  const int y = blockIdx.y * WY + threadIdx.y;
+  if (xt >= gf.nx || y >= gf.ny) return;
+  const int z0 = blockIdx.z * PROLONG_ZB, z1 = min(z0 + PROLONG_ZB, gf.nz);
+  for (int z = z0; z < z1; ++z) {
+    const int o = z * (int)gf.plane + y * gf.pitch + xt;
+    float acc[4];
+    prolong_row(gc, gf, t, coarse, xt, y, z, acc);
+    if (ADD) {
+      const float4 q = *reinterpret_cast<const float4*>(fine + o);
+      acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+    }
+    store4<float>(fine, o, xt, gf.nx, acc);
   }
-  store4<float>(fine, o, xt, gf.nx, acc);
 }
 
 // coarse = R fine: full weighting (mad/itkInterGridOperators.hxx:175-304, tables .h:115-127).  A thread reads
@@ -889,6 +982,30 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict(Geom gf, Geom gc, Tra
   const int xc0 = p.xt >> 1;  // coarse voxels xc0, xc0+1
   restrict_taps(min(xc0, gc.nx - 1), gc.nx, t.cent[0], wxa);
   restrict_taps(min(xc0 + 1, gc.nx - 1), gc.nx, t.cent[0], wxb);
+  if (t.cent[1] == 1 && t.cent[2] == 1 && yc > 0 && yc < gc.ny - 1 && (zc > 0 || !gf.zlo_phys) && (zc < gc.nz - 1 || !gf.zhi_phys)) {
+    // away from the y/z ends of a cell-centred transfer (warp-uniform test): fixed (1/8, 3/8, 3/8, 1/8) taps along y and z, no
+    // clamping; along x the per-thread taps (zero on voxels outside the row, whose stand-in values are finite)
+    const float wt[4] = {.125f, .375f, .375f, .125f};
+    Raw6<float> rw[4][4];
+#pragma unroll
+    for (int kz = 0; kz < 4; ++kz)
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) rw[kz][ky] = issue6(fine, (2 * zc + kz - 1) * (int)gf.plane + (2 * yc + ky - 1) * gf.pitch + p.xl, p);
+    float b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int kz = 0; kz < 4; ++kz)
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const V6<float> v = finish6<float, float>(rw[kz][ky], p);
+        const float wr = wt[ky] * wt[kz];
+        b0 += wr * (wxa[0] * v.v[0] + wxa[1] * v.v[1] + wxa[2] * v.v[2] + wxa[3] * v.v[3]);
+        b1 += wr * (wxb[0] * v.v[2] + wxb[1] * v.v[3] + wxb[2] * v.v[4] + wxb[3] * v.v[5]);
+      }
+    const long long oo = (long long)zc * gc.plane + (long long)yc * gc.pitch + xc0;
+    if (xc0 + 1 < gc.nx) *reinterpret_cast<float2*>(coarse + oo) = make_float2(b0, b1);
+    else if (xc0 < gc.nx) coarse[oo] = b0;
+    return;
+  }
   float a0 = 0.f, a1 = 0.f;
   // All sixteen tap rows are loaded unconditionally (rows outside the image are clamped and carry weight 0):
   // branch-free, so the loads are issued back to back.

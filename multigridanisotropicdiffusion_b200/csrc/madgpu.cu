@@ -174,14 +174,14 @@ dim3 fast_grid(const Geom& g, int wy, int zc) { return dim3((g.nx + fast::TX - 1
 // One streaming pass (MODE_WJ / MODE_RES) over a level; returns the number of CTAs (= partial sums written).
 // ctx->fast_cfg selects the CTA shape / register cap (tuning hook MADGPU_FAST_CFG).
 template <int MODE, typename T, typename UT, typename FT, typename OT>
-size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT* out, double* partials, float omega)
+size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT* out, double* partials, float omega, int uzero = 0)
 {
   const Tensor D = tensor_of(L);
 #define MAD_FAST_LAUNCH(WY, MINB, PF)                                                                                        \
   do {                                                                                                                       \
     const int zc = fast_zc(L.g, WY);                                                                                         \
     const dim3 fg = fast_grid(L.g, WY, zc);                                                                                  \
-    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc, ctx->pf_dist); \
+    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc, ctx->pf_dist, uzero); \
     return (size_t)fg.x * fg.y * fg.z;                                                                                       \
   } while (0)
   if (sizeof(T) == 8) {
@@ -352,7 +352,7 @@ void scatter_slabs(madgpu_ctx* ctx, const Level& L)
   if (ctx->rank == 0) cudaMemcpyAsync(ctx->slab_buf, ctx->gather_buf, cnt * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
 }
 
-void vcycle(madgpu_ctx* ctx, int l);
+void vcycle(madgpu_ctx* ctx, int l, bool zero_guess = false);
 void op_zero(madgpu_ctx* ctx, Level& L, float* p);
 
 // The agglomeration level (last level of a slab context): its right-hand side is gathered onto rank 0, which runs the
@@ -367,8 +367,7 @@ void agglomerated_solve(madgpu_ctx* ctx)
     madgpu_ctx* S = ctx->sub;
     Level& S0 = S->lv[0];
     unpack_slab(S, S0, ctx->gather_buf, S0.f);
-    op_zero(S, S0, S0.u);
-    vcycle(S, 0);
+    vcycle(S, 0, true);  // zero initial guess
     pack_slab(S, S0, S0.u, ctx->gather_buf);
     ctx->launches += S->launches;
     S->launches = 0;
@@ -385,17 +384,22 @@ void op_zero(madgpu_ctx* ctx, Level& L, float* p)
 }
 
 // n_iter smoother iterations on (L.u, L.f); result in L.u (pointers may be swapped with L.tmp).
-void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
+// zero_first: the iterate is identically zero on entry (every V-cycle leg starts like that): the streaming kernels then
+// skip reading it (and the memset that would have produced it); the generic kernels get the memset.
+void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first = false)
 {
   Level& L = ctx->lv[l];
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   const int cls = l == 0 ? MADGPU_K_SMOOTH0 : MADGPU_K_SMOOTHC;
   const Tensor D = tensor_of(L);
+  const bool streaming = use_fast(ctx, L) && (smoother == MADGPU_SMOOTHER_WJ || ctx->gs_fused);
+  if (zero_first && (!streaming || n_iter == 0)) { op_zero(ctx, L, L.u); zero_first = false; }
   for (int it = 0; it < n_iter; ++it) {
-    exchange_halo(ctx, L, L.u);
+    const int uz = zero_first && it == 0;
+    if (!uz) exchange_halo(ctx, L, L.u);
     if (smoother == MADGPU_SMOOTHER_WJ) {
       Scope s(ctx, cls);
-      if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega);
+      if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega, uz);
       else if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       else k_jacobi<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       std::swap(L.u, L.tmp);
@@ -416,7 +420,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
       Scope s(ctx, cls);
       {
         const int zc = fast_zc(L.g, 4);
-        fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
       std::swap(L.u, L.tmp);
     } else if (use_fast(ctx, L) && ctx->gs_fused) {
@@ -424,25 +428,25 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter)
       Scope s(ctx, cls);
       if (ctx->fast_cfg == 1) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<8, 1, false, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 4) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 2, true, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<4, 2, true, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 5) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, true, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<8, 1, true, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 7) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<4, 3, false, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 8) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<8, 1, false, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 6) {
         const int zc = fast_zc(L.g, 2);
-        fast::k_fast_gs<2, 6, false, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<2, 6, false, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist);
+        fast::k_fast_gs<4, 3, false, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
       std::swap(L.u, L.tmp);
     } else {
@@ -479,6 +483,12 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
   Scope s(ctx, MADGPU_K_RESTRICT, norm ? 2 : 1);
   const Tensor D = tensor_of(L);
   double* part = norm ? ctx->partials : nullptr;
+  if (!norm && ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && L.coef16_valid) {
+    // inside a Gauss-Seidel V-cycle: residual with the packed rows the sweeps use
+    const int zc = fast_zc(L.g, 4);
+    fast::k_coef_residual<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, out, zc, ctx->pf_dist);
+    return;
+  }
   if (use_fast(ctx, L)) {
     const size_t nb = launch_fast<fast::MODE_RES, float, float, float, float>(ctx, L, L.u, L.f, out, part, 0.f);
     if (norm) reduce_partials(ctx, nb);
@@ -551,7 +561,7 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
   if constexpr (std::is_same<TO, float>::value) {
     if (use_fast(ctx, F)) {
       constexpr int WY = 8;
-      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, F.g.nz);
+      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, (F.g.nz + fast::PROLONG_ZB - 1) / fast::PROLONG_ZB);
       fast::k_fast_prolong<ADD, WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
       return;
     }
@@ -592,9 +602,11 @@ void op_coarse_solve(madgpu_ctx* ctx)
 
 // V-cycle at level l on (L.u, L.f): itkMultigridAnisotropicDiffusionImageFilter.hxx:341-493 without the
 // reference's logging-only residual/norm passes (:389-411, :437-439, :464-487).
-void vcycle(madgpu_ctx* ctx, int l)
+// zero_guess: the iterate of level l is identically zero on entry and need not have been written (the correction
+// equations of the coarser levels, …Filter.hxx:415-416, and of level 0 in defect-correction form).
+void vcycle(madgpu_ctx* ctx, int l, bool zero_guess)
 {
-  if (l == ctx->nlevels - 1) {  // :356-371
+  if (l == ctx->nlevels - 1) {  // :356-371  (both solvers overwrite the whole iterate)
     if (ctx->world > 1) agglomerated_solve(ctx);
     else op_coarse_solve(ctx);
     return;
@@ -602,11 +614,10 @@ void vcycle(madgpu_ctx* ctx, int l)
   Level& L = ctx->lv[l];
   Level& C = ctx->lv[l + 1];
   const int nu = ctx->p.iterations_per_grid;
-  op_smooth(ctx, l, ctx->p.smoother, nu);                 // :384-387
+  op_smooth(ctx, l, ctx->p.smoother, nu, zero_guess);     // :384-387
   op_residual32(ctx, l, L.tmp, false);                    // :389 (last one only)
   op_restrict<float>(ctx, l, L.tmp, C.f);                 // :413
-  op_zero(ctx, C, C.u);                                   // :415-416
-  vcycle(ctx, l + 1);                                     // :418-420
+  vcycle(ctx, l + 1, true);                               // :415-420, zero coarse guess
   op_prolong<float, true>(ctx, l, C.u, L.u);              // :422-435
   op_smooth(ctx, l, ctx->p.smoother, nu);                 // :460-463
 }
@@ -624,9 +635,8 @@ void op_axpy(madgpu_ctx* ctx)
 void outer_iteration(madgpu_ctx* ctx, bool smoother_only)
 {
   Level& L = ctx->lv[0];
-  op_zero(ctx, L, L.u);
-  if (smoother_only) op_smooth(ctx, 0, ctx->p.smoother, 1);  // …Filter.hxx:213
-  else vcycle(ctx, 0);                                       // …Filter.hxx:235
+  if (smoother_only) op_smooth(ctx, 0, ctx->p.smoother, 1, true);  // …Filter.hxx:213
+  else vcycle(ctx, 0, true);                                       // …Filter.hxx:235
   op_axpy(ctx);
   op_residual64(ctx, L.f, nullptr);                          // …Filter.hxx:215-217 / :237-239
 }
