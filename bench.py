@@ -237,9 +237,10 @@ def run_ours(args):
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        ent = prof.get("smooth0", {})
-        if ent.get("size") == n and ent.get("smoother") == args.smoother:
-            traffic = ent.get("dram_bytes_per_launch")
+        for key in ("smooth0", "smooth0_" + args.smoother):
+            ent = prof.get(key, {})
+            if ent.get("size") == n and ent.get("smoother") == args.smoother and world == 1:
+                traffic = ent.get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "level-0 smoother sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
