@@ -13,8 +13,9 @@ level-0 residual-norm stop test and its read-back, exactly one pass of the refer
   e2e    : the same metric through the filter call with HOST (pinned) buffers: one DiffusionStep
            (SetDiffusionTensor + 4 time steps to tolerance 1e-10), tensor/image H2D and result D2H
            inside the timed region; value = voxels x cycles executed / wall time
-  roofline: level-0 smoother sweep, 36 B/voxel algorithmic over the
-           CUDA-event time of those launches, against the measured HBM copy peak
+  roofline: level-0 smoother sweep, 36 B/voxel algorithmic (u, f, u', six tensor planes) over the
+           CUDA-event time of those launches, against the measured HBM copy peak.  (The Gauss-Seidel sweep reads
+           pre-evaluated fp16 operator rows, 20 B/voxel, instead of the 24 B of tensor planes: ncu traffic 32 B/voxel.)
   cpu_baseline: the oracle restatement of the reference (lexicographic GS, double, 1 thread, with the
            reference's redundant residual/norm passes) timed on a bounded sample of the same workload
 """
