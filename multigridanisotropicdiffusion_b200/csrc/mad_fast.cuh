@@ -830,6 +830,126 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
   }
 }
 
+// Row-pair variant of k_coef_gs: one warp owns an even row and the odd row above it and relaxes them one after the other, so
+// no warp idles while the other row parity is being relaxed (in k_coef_gs half of a CTA's warps wait at the phase barrier).
+// Same ordering and tile semantics (tile = 128 x 2*WP x zc); needs an even ny.  Per plane step a thread loads the four rows
+// y0-1 .. y0+2 of plane z+1 (two row loads per relaxed row instead of three), the packed rows and f of its two rows.
+struct URows4 {
+  V6<float> r[4];  // rows y0-1, y0 (even), y0+1 (odd), y0+2
+};
+__device__ __forceinline__ float offdiag16_rows(const CoefRaw& c, const URows4& m, const URows4& q, const URows4& n, int row, int j)
+{
+  // `row` = 1 (even row) or 2 (odd row): its y-neighbours are the slots row-1 and row+1
+  float s = coef_at(c, 1, j) * q.r[row].v[j + 2] + coef_at(c, 2, j) * q.r[row].v[j] + coef_at(c, 3, j) * q.r[row + 1].v[j + 1] +
+            coef_at(c, 4, j) * q.r[row - 1].v[j + 1];
+  s += coef_at(c, 7, j) * ((q.r[row + 1].v[j + 2] - q.r[row - 1].v[j + 2]) - (q.r[row + 1].v[j] - q.r[row - 1].v[j]));
+  s += coef_at(c, 5, j) * n.r[row].v[j + 1] + coef_at(c, 6, j) * m.r[row].v[j + 1];
+  s += coef_at(c, 8, j) * ((n.r[row].v[j + 2] - m.r[row].v[j + 2]) - (n.r[row].v[j] - m.r[row].v[j]));
+  s += coef_at(c, 9, j) * ((n.r[row + 1].v[j + 1] - m.r[row + 1].v[j + 1]) - (n.r[row - 1].v[j + 1] - m.r[row - 1].v[j + 1]));
+  return s;
+}
+
+template <int WP, int MINB>
+__global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
+                                                              const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero)
+{
+  __shared__ float4 sh[2][2 * WP][32];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  Pos p;
+  p.lane = lane;
+  p.xt = blockIdx.x * TX + lane * 4;
+  p.xl = p.xt < g.nx ? p.xt : 0;
+  p.jl = g.nx - 1 - p.xt;
+  p.edge = lane == 0 || lane == 31;
+  p.dh = (lane == 0 ? max(p.xt - 1, 0) : min(p.xt + 4, g.nx - 1)) - p.xl;
+  p.xb = p.xt == 0 || (p.jl >= 0 && p.jl < 4);
+  const int ytile = blockIdx.y * 2 * WP;
+  const int y0 = ytile + 2 * w;           // even row of this warp; ny is even, so y0 + 1 exists whenever y0 does
+  const bool valid = y0 < g.ny;
+  const int yb = valid ? y0 : 0;
+  // image rows behind the four slots (node mirror at the y ends) and the tile rows that publish their new values
+  const int rA = yb == 0 ? 1 : yb - 1, rD = yb + 2 >= g.ny ? g.ny - 2 : yb + 2;
+  const int tA = rA - ytile, tD = rD - ytile;
+  const bool has_A = tA >= 0 && tA < 2 * WP, has_D = tD >= 0 && tD < 2 * WP;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
+  const int xo = p.xl;
+  const int oA = rA * g.pitch + xo, oB = yb * g.pitch + xo, oC = (yb + 1) * g.pitch + xo, oD = rD * g.pitch + xo;
+  URows4 um, uc, up;
+  auto zero_rows = [](URows4& R) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) R.r[i].v[k] = 0.f;
+  };
+  auto load_rows = [&](int zplane, URows4& R) {
+    const int b = zplane * (int)g.plane;
+    const Raw6<float> a0 = issue6(u, b + oA, p), a1 = issue6(u, b + oB, p), a2 = issue6(u, b + oC, p), a3 = issue6(u, b + oD, p);
+    R.r[0] = finish6<float, float>(a0, p); R.r[1] = finish6<float, float>(a1, p);
+    R.r[2] = finish6<float, float>(a2, p); R.r[3] = finish6<float, float>(a3, p);
+    if (p.xb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mirror_x(R.r[i], p.xt, p.jl);
+    }
+  };
+  if (uzero) { zero_rows(um); zero_rows(uc); }
+  else { load_rows(zmirror_lo(g, z0), um); load_rows(z0, uc); }
+  for (int z = z0; z < z1; ++z) {
+    const int cb = z & 1, pb = cb ^ 1;
+    const int zb = z * (int)g.plane;
+    // ---- loads of this plane step ----
+    const CoefRaw cB = issue_coef(coef, g, p, yb, z), cC = issue_coef(coef, g, p, yb + 1, z);
+    const Raw4<float> rfB = issue4(f, zb + oB), rfC = issue4(f, zb + oC);
+    if (uzero) zero_rows(up);
+    else load_rows(zmirror_hi(g, z), up);
+    const V4<float> fB = finish4<float>(rfB), fC = finish4<float>(rfC);
+    // plane z-1 was relaxed one step ago: the neighbouring warps' rows come from the tile's row buffer
+    if (z > z0) {
+      if (has_A) { const float4 q = sh[pb][tA][lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
+      if (has_D) { const float4 q = sh[pb][tD][lane]; um.r[3].v[1] = q.x; um.r[3].v[2] = q.y; um.r[3].v[3] = q.z; um.r[3].v[4] = q.w; }
+    }
+    if (z == g.nz - 1 && g.zhi_phys) up = um;  // mirrored plane z+1 == plane z-1, already relaxed
+    // relax one of the warp's two rows: even x, then odd x (x-neighbours through shuffles)
+    auto relax = [&](int row, const CoefRaw& c, const V4<float>& fv, int orow) {
+      const float n0 = fv.v[0] * coef_at(c, 0, 0) - offdiag16_rows(c, um, uc, up, row, 0);
+      const float n2 = fv.v[2] * coef_at(c, 0, 2) - offdiag16_rows(c, um, uc, up, row, 2);
+      uc.r[row].v[1] = n0; uc.r[row].v[3] = n2;
+      {
+        const float r = __shfl_down_sync(FULL, n0, 1);
+        if (lane < 31) uc.r[row].v[5] = r;
+        if (p.xb) mirror_x(uc.r[row], p.xt, p.jl);
+      }
+      const float n1 = fv.v[1] * coef_at(c, 0, 1) - offdiag16_rows(c, um, uc, up, row, 1);
+      const float n3 = fv.v[3] * coef_at(c, 0, 3) - offdiag16_rows(c, um, uc, up, row, 3);
+      uc.r[row].v[2] = n1; uc.r[row].v[4] = n3;
+      {
+        const float l = __shfl_up_sync(FULL, n3, 1);
+        if (lane > 0) uc.r[row].v[0] = l;
+        if (p.xb) mirror_x(uc.r[row], p.xt, p.jl);
+      }
+      sh[cb][2 * w + row - 1][lane] = make_float4(n0, n1, n2, n3);
+      const float res[4] = {n0, n1, n2, n3};
+      if (p.xt < g.nx) store4<float>(out, zb + orow, p.xt, g.nx, res);
+    };
+    // phase 1: even rows (rows y0-1 and y0+1 of this plane still hold the previous sweep)
+    if (valid) relax(1, cB, fB, oB);
+    __syncthreads();
+    // phase 2: odd rows; row y0+2 (an even row) was relaxed in phase 1 by the next warp
+    if (valid) {
+      if (has_D) {
+        const float* sd = reinterpret_cast<const float*>(&sh[cb][tD][0]);
+        const float4 q = reinterpret_cast<const float4*>(sd)[lane];
+        uc.r[3].v[1] = q.x; uc.r[3].v[2] = q.y; uc.r[3].v[3] = q.z; uc.r[3].v[4] = q.w;
+        if (lane > 0) uc.r[3].v[0] = sd[lane * 4 - 1];
+        if (lane < 31) uc.r[3].v[5] = sd[lane * 4 + 4];
+        if (p.xb) mirror_x(uc.r[3], p.xt, p.jl);
+      }
+      relax(2, cC, fC, oC);
+    }
+    __syncthreads();
+    um = uc; uc = up;
+  }
+}
+
 // r = f - A u from the packed rows (the residual that feeds the restriction INSIDE a Gauss-Seidel V-cycle: it is taken
 // with the same fp16-rounded operator the sweeps relax, so the inner cycle is a consistent multigrid cycle for that
 // operator; the outer defect and the stop test keep the exact rows).  Same marching structure, no phases.

@@ -111,6 +111,7 @@ struct madgpu_ctx {
   int total_levels;    // levels of the whole hierarchy (distributed + serial)
   int gsize[MADGPU_MAX_LEVELS][3], gcent[MADGPU_MAX_LEVELS][3];  // global level schedule
   int pf_dist;      // L2 prefetch distance (planes) of the streaming kernels, 0 = off
+  int gs_pairs;     // packed-row Gauss-Seidel: one warp per row pair (k_coef_gs2) where ny is even
   int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
@@ -160,6 +161,7 @@ bool use_fast(const madgpu_ctx* ctx, const Level& L)
 {
   return ctx->dim == 3 && L.g.nx >= ctx->fast_min_nx && L.g.nz >= 3 && L.g.ny >= 3 && L.elems < (1ull << 31);  // 32-bit element offsets
 }
+bool gs_pairs(const madgpu_ctx* ctx, const Level& L) { return ctx->gs_pairs && L.g.ny % 2 == 0 && L.g.ny >= 4; }
 // planes per CTA: enough CTAs for ~8 waves of the resident set, at least 8 planes so that the two start-up planes stay cheap
 int fast_zc(const Geom& g, int wy)
 {
@@ -418,7 +420,10 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
         L.coef16_valid = true;
       }
       Scope s(ctx, cls);
-      {
+      if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
+        const int zc = fast_zc(L.g, 8);
+        fast::k_coef_gs2<4, 3><<<fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+      } else {
         const int zc = fast_zc(L.g, 4);
         fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
@@ -1165,6 +1170,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
     e = getenv("MADGPU_PF_DIST");
     ctx->pf_dist = e ? atoi(e) : 2;
+    e = getenv("MADGPU_GS_PAIRS");
+    ctx->gs_pairs = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_COEF16");
     ctx->gs_coef16 = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_FUSED");
@@ -1512,7 +1519,7 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (!ctx || !tile || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
   const Level& L = ctx->lv[level];
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
-    const int wy = ctx->gs_coef16 ? 4 : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
+    const int wy = ctx->gs_coef16 ? (gs_pairs(ctx, L) ? 8 : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
     tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level

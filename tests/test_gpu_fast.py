@@ -134,15 +134,19 @@ GS_CASES = [
     ((21, 11, 140), (0.3125, 0.3125, 0.5), 0.1),  # several z chunks? (tile from gs_tile)
     ((23, 25, 27), (0.3125, 0.3125, 0.5), 0.1),
     ((9, 6, 131), (1.0, 0.7, 1.3), 0.1),
+    ((14, 18, 200), (1.0, 1.0, 1.0), 0.1),        # even ny > 8: several row-pair tiles
 ]
 
 
-@pytest.fixture(params=[(0, 0), (1, 0), (7, 0), (8, 0), (0, 1)], ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}")
+@pytest.fixture(params=[(0, 0, 0), (1, 0, 0), (7, 0, 0), (8, 0, 0), (0, 1, 0), (0, 1, 1)],
+                ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}{'-pairs' if c[2] else ''}")
 def gs_env(request, monkeypatch):
-    """(kernel variant, packed fp16 operator rows): the default is (0, 1); the exact-row variants pin the ordering."""
+    """(kernel variant, packed fp16 operator rows, one warp per row pair): the default is (0, 1, 1); the exact-row
+    variants pin the ordering to fp32 rounding."""
     monkeypatch.setenv("MADGPU_FAST_MIN_NX", "0")
     monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param[0]))
     monkeypatch.setenv("MADGPU_GS_COEF16", str(request.param[1]))
+    monkeypatch.setenv("MADGPU_GS_PAIRS", str(request.param[2]))
     return request.param
 
 
