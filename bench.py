@@ -134,22 +134,57 @@ def cpu_reference_run(size: int, nu: int, smoother: int, steps: int, warmup: int
     return dict(mvox_s=n * steps / dt / 1e6, s_per_cycle=dt / steps, setup_s=setup_s, relres=relres, voxels=n)
 
 
+def _cpu_worker(a):
+    size, nu, smoother, steps, warmup = a
+    return cpu_reference_run(size, nu, smoother, steps, warmup)
+
+
+def cpu_reference_all_cores(size: int, nu: int, smoother: int, steps: int, warmup: int, procs: int):
+    """The reference solver is single-threaded by construction (GenerateData, not ThreadedGenerateData; its Gauss-Seidel
+    sweep is lexicographic), so "all the host cores" means one independent solve per core: `procs` processes each run the
+    same bounded sample concurrently and the aggregate voxel rate is reported."""
+    import multiprocessing as mp
+    if procs <= 1:
+        r = cpu_reference_run(size, nu, smoother, steps, warmup)
+        r["procs"] = 1
+        return r
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        rs = pool.map(_cpu_worker, [(size, nu, smoother, steps, warmup)] * procs)
+    wall = time.perf_counter() - t0
+    slowest = max(r["s_per_cycle"] for r in rs)
+    n = size ** 3
+    return dict(mvox_s=procs * n / slowest / 1e6, s_per_cycle=slowest, setup_s=max(r["setup_s"] for r in rs), relres=rs[0]["relres"],
+                voxels=n, procs=procs, wall_s=wall, single_core_mvox_s=rs[0]["mvox_s"])
+
+
+def host_procs(limit=16):
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, limit))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     nu, sm = args.nu, (0 if args.smoother == "gs" else 1)
-    r = cpu_reference_run(args.cpu_size, nu, sm, args.steps, args.warmup)
+    procs = host_procs()
+    r = cpu_reference_all_cores(args.cpu_size, nu, sm, args.steps, args.warmup, procs)
     line = {
         "impl": "reference",
         "metric": "3D VED V-cycle Mvoxels/s at 512^3", "value": r["mvox_s"], "unit": "Mvoxel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_cycle"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, "replicas" if args.gpus > 1 else "single"),
-        "cpu_baseline": {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": 1, "kind": "port",
-                         "sample": f"{args.cpu_size}^3 sub-volume of the same phantom/tensor, {args.steps} V({nu},{nu}) cycles, "
-                                   "oracle restatement in faithful mode (reference cannot be built: ITK/VXL absent), setup "
-                                   f"{r['setup_s']:.1f}s excluded"},
+        "cpu_baseline": {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": "port",
+                         "sample": f"{r['procs']} concurrent single-threaded solves (the reference has no threading), each a {args.cpu_size}^3 "
+                                   f"volume of the same phantom/tensor, {args.steps} V({nu},{nu}) cycles of the oracle port in faithful mode "
+                                   "(bit-identical to the reference headers compiled against the stand-in ITK, which are slower); "
+                                   f"setup {r['setup_s']:.1f}s excluded; one core alone: {r.get('single_core_mvox_s', r['mvox_s']):.2f} Mvoxel/s"},
         "e2e": {"value": r["mvox_s"], "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -296,10 +331,11 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.cpu_size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0)
-        cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": 1, "kind": "port",
-               "sample": f"{args.cpu_size}^3 sub-volume of the same phantom/tensor, {args.cpu_steps} V({nu},{nu}) cycles of the oracle "
-                         f"restatement in faithful mode (lexicographic GS, double, 1 thread; setup {r['setup_s']:.1f}s excluded)"}
+        r = cpu_reference_all_cores(args.cpu_size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0, host_procs())
+        cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": "port",
+               "sample": f"{r['procs']} concurrent single-threaded solves (the reference has no threading), each a {args.cpu_size}^3 volume of "
+                         f"the same phantom/tensor, {args.cpu_steps} V({nu},{nu}) cycles of the oracle port in faithful mode (lexicographic GS, "
+                         f"double; setup {r['setup_s']:.1f}s excluded); one core alone: {r.get('single_core_mvox_s', r['mvox_s']):.2f} Mvoxel/s"}
 
     if rank == 0:
         line = {
