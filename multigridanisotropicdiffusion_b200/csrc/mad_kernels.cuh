@@ -467,15 +467,20 @@ __global__ void k_pitched_to_dense(Geom g, const TI* __restrict__ in, TO* __rest
   out[((long long)z * g.ny + y) * g.nx + x] = cast_out<TO>((double)in[(long long)z * g.plane + (long long)y * g.pitch + x]);
 }
 
-// u64 += e32  (correction add of the outer defect-correction loop)
-__global__ void k_axpy_f64_f32(Geom g, double* __restrict__ u, const float* __restrict__ e)
+// u64 += e32  (correction add of the outer defect-correction loop); four voxels per thread (rows are padded to a
+// multiple of 32 elements, so the 16/32-byte accesses never leave the row's allocation)
+__global__ void __launch_bounds__(256) k_axpy_f64_f32(Geom g, double* __restrict__ u, const float* __restrict__ e)
 {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int z = blockIdx.z * blockDim.z + threadIdx.z;
-  if (x >= g.nx || y >= g.ny || z >= g.nz) return;
+  const int z = blockIdx.z;
+  if (x >= g.nx || y >= g.ny) return;
   const long long c = (long long)z * g.plane + (long long)y * g.pitch + x;
-  u[c] += (double)e[c];
+  const float4 q = *reinterpret_cast<const float4*>(e + c);
+  double2 a = *reinterpret_cast<double2*>(u + c), b = *reinterpret_cast<double2*>(u + c + 2);
+  a.x += (double)q.x; a.y += (double)q.y; b.x += (double)q.z; b.y += (double)q.w;
+  *reinterpret_cast<double2*>(u + c) = a;
+  *reinterpret_cast<double2*>(u + c + 2) = b;
 }
 
 // AoS tensor chunk (ITK SymmetricSecondRankTensor buffer) -> SoA fp32 pitched planes.

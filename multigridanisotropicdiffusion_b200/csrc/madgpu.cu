@@ -101,6 +101,8 @@ struct madgpu_ctx {
   int64_t launches;
   // z-slab decomposition (world > 1): this context owns planes [lv[l].zb, lv[l].zb + lv[l].n[2]) of levels 0..nlevels-1;
   // the last of them (the agglomeration level) is gathered to rank 0, whose `sub` context holds the rest of the hierarchy
+  void* stage[2];        // persistent host<->device staging (tensor chunks, image), grown on demand
+  size_t stage_bytes[2];
   int rank, world;
   std::string sticky;  // first collective error inside an operator
   bool borrowed_stream;  // sub-context of a slab context: runs on the parent's stream
@@ -630,7 +632,7 @@ void vcycle(madgpu_ctx* ctx, int l, bool zero_guess)
 void op_axpy(madgpu_ctx* ctx)
 {
   Level& L = ctx->lv[0];
-  const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
+  const dim3 b(32, 8, 1), g((L.g.nx + 127) / 128, (L.g.ny + 7) / 8, L.g.nz);
   Scope s(ctx, MADGPU_K_MISC);
   k_axpy_f64_f32<<<g, b, 0, ctx->stream>>>(L.g, ctx->u64, L.u);
 }
@@ -920,6 +922,15 @@ int finish_tensor(madgpu_ctx* ctx)
   return 0;
 }
 
+int ensure_stage(madgpu_ctx* ctx, int i, size_t bytes)
+{
+  if (ctx->stage_bytes[i] >= bytes) return 0;
+  if (ctx->stage[i]) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->stage[i]); ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0; }
+  CU(cudaMalloc(&ctx->stage[i], bytes));
+  ctx->stage_bytes[i] = bytes;
+  return 0;
+}
+
 template <typename T>
 int set_tensor_host(madgpu_ctx* ctx, const T* aos)
 {
@@ -934,7 +945,9 @@ int set_tensor_host(madgpu_ctx* ctx, const T* aos)
   cudaEvent_t done[2];
   const long long cap = std::min(chunk, nvox);
   for (int i = 0; i < 2; ++i) {
-    CU(cudaMalloc((void**)&stage[i], (size_t)cap * nc * sizeof(T)));
+    const int rc = ensure_stage(ctx, i, (size_t)cap * nc * sizeof(T));
+    if (rc) return rc;
+    stage[i] = (T*)ctx->stage[i];
     CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
   }
   int k = 0;
@@ -949,7 +962,7 @@ int set_tensor_host(madgpu_ctx* ctx, const T* aos)
     CU(cudaEventRecord(done[k], ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < 2; ++i) { cudaFree(stage[i]); cudaEventDestroy(done[i]); }
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
   const int rc = finish_tensor(ctx);
   ctx->st.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return rc;
@@ -1163,6 +1176,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
   ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
+  ctx->stage[0] = ctx->stage[1] = nullptr; ctx->stage_bytes[0] = ctx->stage_bytes[1] = 0;
   ctx->rank = rank; ctx->world = world; ctx->comm = nullptr; ctx->sub = nullptr; ctx->gather_buf = nullptr; ctx->slab_buf = nullptr;
   ctx->borrowed_stream = shared_stream != nullptr;
   {
@@ -1306,6 +1320,7 @@ void madgpu_destroy(madgpu_ctx* ctx)
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_c) cudaEventDestroy(ctx->ev_c);
+  for (int i = 0; i < 2; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
   if (ctx->sub) madgpu_destroy(ctx->sub);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
   if (ctx->slab_buf) cudaFree(ctx->slab_buf);
@@ -1357,16 +1372,17 @@ int madgpu_solve_cast(madgpu_ctx* ctx, int32_t in_type, const void* in, int32_t 
   begin_stats(ctx);
   Level& L = ctx->lv[0];
   const size_t nvox = (size_t)L.n[0] * L.n[1] * L.n[2];
-  void* stage = nullptr;
   const size_t sb = nvox * std::max(pix_size(in_type), pix_size(out_type));
-  CU(cudaMalloc(&stage, sb));
+  rc = ensure_stage(ctx, 0, sb);
+  if (rc) return rc;
+  void* stage = ctx->stage[0];
   auto t0 = std::chrono::steady_clock::now();
   cudaError_t e = cudaMemcpyAsync(stage, in, nvox * pix_size(in_type), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) { rc = stage_input(ctx, in_type, stage); e = cudaStreamSynchronize(ctx->stream); }
   ctx->st.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (e != cudaSuccess || rc) { cudaFree(stage); return rc ? rc : fail(ctx, MADGPU_ECUDA, "input upload: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess || rc) return rc ? rc : fail(ctx, MADGPU_ECUDA, "input upload: %s", cudaGetErrorString(e));
   rc = run_steps(ctx);
-  if (rc) { cudaFree(stage); return rc; }
+  if (rc) return rc;
   t0 = std::chrono::steady_clock::now();
   rc = stage_output(ctx, out_type, stage);
   if (!rc) {
@@ -1374,7 +1390,6 @@ int madgpu_solve_cast(madgpu_ctx* ctx, int32_t in_type, const void* in, int32_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
   ctx->st.d2h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  cudaFree(stage);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(ctx, MADGPU_ECUDA, "output download: %s", cudaGetErrorString(e));
   end_stats(ctx, stats);
