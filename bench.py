@@ -225,6 +225,7 @@ def run_ours(args):
     nu = args.nu
     smoother = MadSolver.GS if args.smoother == "gs" else MadSolver.WJ
     slab_mode = world > 1 and not args.replicas
+    peer_halo = False
     if slab_mode:
         # ONE volume cut into z-slabs, one per GPU (strong scaling): NCCL halo exchange inside libmadgpu.so
         from multigridanisotropicdiffusion_b200 import slabs
@@ -233,6 +234,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         s = MadSolver(shape, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, tolerance=0.0,
                       max_cycles=1 << 20, device=local_rank, rank=rank, world_size=world, nccl_id=slabs.create_unique_id())
+        peer_halo = (not args.nccl_halo) and slabs.enable_peer_halo(s)
     else:
         img, D = phantom.vessel_phantom(shape, device=dev)
         torch.cuda.synchronize()
@@ -348,7 +350,8 @@ def run_ours(args):
             "metric": "3D VED V-cycle Mvoxels/s at 512^3", "value": value, "unit": "Mvoxel/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if (slab_mode or world == 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, f"z-slabs: {world} x {shape[0]} planes, NCCL halo exchange per sweep, levels <= 64^3 agglomerated on rank 0"
+            "config": workload_config(args, f"z-slabs: {world} x {shape[0]} planes, halo = " + ("NVLink peer stores from the producing kernels + stream memory ops"
+                                      if peer_halo else "NCCL send/recv per sweep") + ", levels <= 64^3 agglomerated on rank 0"
                                       if slab_mode else "independent replicas (one volume per GPU)" if world > 1 else "single GPU"),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed), "clocks": clocks,
             "relres_after_timed_cycles": float(relres[-1]) if len(relres) else None, "wall_ms_timed_region": wall_ms,
@@ -371,6 +374,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="N > 1: keep the NCCL send/recv halo exchange instead of peer stores")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent volumes per GPU instead of z-slabs of one volume")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

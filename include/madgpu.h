@@ -123,6 +123,14 @@ const char *madgpu_last_error(const madgpu_ctx *ctx); /* ctx may be NULL: error 
  *   id128: 128 bytes from madgpu_nccl_unique_id() on one rank, distributed by the caller (MPI, torch.distributed, ...). */
 int madgpu_nccl_unique_id(void *id128);
 int madgpu_create_slab(const madgpu_params *p, const void *nccl_unique_id, madgpu_ctx **out);
+/* Optional, after madgpu_create_slab on every rank: peer-memory halo.  Each rank exports the CUDA IPC handles of its
+ * level fields (madgpu_ipc_export: pass blob = NULL to learn the size), the caller moves the blobs between the ranks,
+ * and every rank imports the blobs of rank-1 and rank+1 (NULL where there is none).  From then on the kernel that
+ * produces a field stores its two boundary planes straight into the neighbours' ghost planes over NVLink and the stream
+ * bumps an arrival counter in the neighbours' memory (cuStreamWriteValue32 / cuStreamWaitValue32): no separate exchange
+ * step.  NCCL send/recv remains the fallback (tensor set-up, agglomeration level, contexts that do not import). */
+int madgpu_ipc_export(madgpu_ctx *ctx, void *blob, size_t capacity, size_t *needed);
+int madgpu_ipc_import(madgpu_ctx *ctx, const void *blob_lower, const void *blob_upper);
 /* planes [z_begin, z_begin + z_count) of `level` held by this context; global_nz = planes of the whole level.
  * Valid for the levels this context holds (all of them when world_size == 1). */
 int madgpu_slab(const madgpu_ctx *ctx, int32_t level, int32_t *z_begin, int32_t *z_count, int32_t *global_nz);

@@ -246,6 +246,14 @@ __device__ __forceinline__ void prefetch_plane(const Prefetch& P, int z)
   if (P.b) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b + P.stride * z));
 }
 
+// first / last plane of a slab: the same row also goes to the neighbour's ghost plane (peer store over NVLink)
+template <typename OT>
+__device__ __forceinline__ void store_ghosts(const Geom& g, int z, int rowoff, int xt, const float v[4])
+{
+  if (z == 0 && g.glo) store4<OT>(reinterpret_cast<OT*>(g.glo), rowoff, xt, g.nx, v);
+  if (z == g.nz - 1 && g.ghi) store4<OT>(reinterpret_cast<OT*>(g.ghi), rowoff, xt, g.nx, v);
+}
+
 __device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 
@@ -511,7 +519,10 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
           if (p.xt + j < g.nx) sq += (double)r * (double)r;
         }
       }
-      if (MODE != MODE_COEF && out && p.xt < g.nx) store4<OT>(out, oc, p.xt, g.nx, res);
+      if (MODE != MODE_COEF && out && p.xt < g.nx) {
+        store4<OT>(out, oc, p.xt, g.nx, res);
+        store_ghosts<OT>(g, z, rowo, p.xt, res);
+      }
       if (MODE == MODE_COEF && p.xt < g.nx) {
         __half2 h[10][2];
 #pragma unroll
@@ -657,7 +668,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, con
       }
       sh[cb][w][p.lane] = make_float4(n0, n1, n2, n3);
       const float res[4] = {n0, n1, n2, n3};
-      if (p.xt < g.nx) store4<float>(out, oc, p.xt, g.nx, res);
+      if (p.xt < g.nx) { store4<float>(out, oc, p.xt, g.nx, res); store_ghosts<float>(g, z, rowo, p.xt, res); }
     };
     const bool last_plane = z == g.nz - 1 && g.zhi_phys;  // the mirrored plane z+1 IS plane z-1, which has already been updated
     if (SPLIT) {
@@ -822,7 +833,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
         }
         sh[cb][w][p.lane] = make_float4(n0, n1, n2, n3);
         const float res[4] = {n0, n1, n2, n3};
-        if (p.xt < g.nx) store4<float>(out, oc, p.xt, g.nx, res);
+        if (p.xt < g.nx) { store4<float>(out, oc, p.xt, g.nx, res); store_ghosts<float>(g, z, rowo, p.xt, res); }
       }
       __syncthreads();
     }
@@ -928,7 +939,7 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
       }
       sh[cb][2 * w + row - 1][lane] = make_float4(n0, n1, n2, n3);
       const float res[4] = {n0, n1, n2, n3};
-      if (p.xt < g.nx) store4<float>(out, zb + orow, p.xt, g.nx, res);
+      if (p.xt < g.nx) { store4<float>(out, zb + orow, p.xt, g.nx, res); store_ghosts<float>(g, z, orow, p.xt, res); }
     };
     // phase 1: even rows (rows y0-1 and y0+1 of this plane still hold the previous sweep)
     if (valid) relax(1, cB, fB, oB);
@@ -985,7 +996,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_residual(Geom g, const u
       // rows are stored divided by diag: A u = (u + sum_k c_k u_k) / inv
       res[j] = __fdividef(fv.v[j] * inv - uc.r[1].v[j + 1] - offdiag16(c, um, uc, up, j), inv);
     }
-    if (p.xt < g.nx) store4<float>(out, oc, p.xt, g.nx, res);
+    if (p.xt < g.nx) { store4<float>(out, oc, p.xt, g.nx, res); store_ghosts<float>(g, z, rowo, p.xt, res); }
     um = uc; uc = up;
   }
 }
@@ -1077,6 +1088,7 @@ __global__ void __launch_bounds__(32 * WY) k_fast_prolong(Geom gc, Geom gf, Tran
       acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
     }
     store4<float>(fine, o, xt, gf.nx, acc);
+    store_ghosts<float>(gf, z, y * gf.pitch + xt, xt, acc);
   }
 }
 

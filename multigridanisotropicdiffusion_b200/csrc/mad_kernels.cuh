@@ -30,6 +30,11 @@ struct Geom {
   int zlo_phys;        // local z = 0 is the physical (Neumann) boundary
   int zhi_phys;        // local z = nz-1 is the physical boundary
   int z0;              // global z of local plane 0 (colour parity)
+  // z-slab decomposition with peer access: where a kernel that PRODUCES a field also stores its first / last plane --
+  // the neighbour slab's upper / lower ghost plane of the same field, mapped through CUDA IPC (NVLink peer stores);
+  // null on a single GPU, at the outer slabs and on the NCCL path.  Set per launch by the host.
+  void* glo;
+  void* ghi;
   float wx, wy, wz;    // dt / h_d^2
   float cxy, cxz, cyz; // dt / (2 h_a h_b)
   float bxx, bxy, bxz, byy, byz, bzz;  // dt / (4 h_d h_d2)
@@ -481,6 +486,17 @@ __global__ void __launch_bounds__(256) k_axpy_f64_f32(Geom g, double* __restrict
   a.x += (double)q.x; a.y += (double)q.y; b.x += (double)q.z; b.y += (double)q.w;
   *reinterpret_cast<double2*>(u + c) = a;
   *reinterpret_cast<double2*>(u + c + 2) = b;
+  double* gp = z == 0 ? (double*)g.glo : z == g.nz - 1 ? (double*)g.ghi : nullptr;
+  if (gp) {
+    const long long r = (long long)y * g.pitch + x;
+    *reinterpret_cast<double2*>(gp + r) = a;
+    *reinterpret_cast<double2*>(gp + r + 2) = b;
+  }
+  if (g.nz == 1 && g.glo && g.ghi) {  // a one-plane slab feeds both neighbours
+    const long long r = (long long)y * g.pitch + x;
+    *reinterpret_cast<double2*>((double*)g.ghi + r) = a;
+    *reinterpret_cast<double2*>((double*)g.ghi + r + 2) = b;
+  }
 }
 
 // AoS tensor chunk (ITK SymmetricSecondRankTensor buffer) -> SoA fp32 pitched planes.

@@ -103,6 +103,15 @@ struct madgpu_ctx {
   // the last of them (the agglomeration level) is gathered to rank 0, whose `sub` context holds the rest of the hierarchy
   void* stage[2];        // persistent host<->device staging (tensor chunks, image), grown on demand
   size_t stage_bytes[2];
+  // peer-memory halo (z-slabs with CUDA IPC): every shareable allocation of this context, the neighbours' mappings of
+  // the same allocations, two arrival counters the neighbours write with stream memory operations
+  struct Shared { void* local; size_t bytes; void* lo; void* hi; uint32_t produced; };
+  std::vector<Shared> shared;
+  uint32_t* flags;        // [0] written by the lower neighbour, [1] by the upper one
+  uint32_t* flags_lo;     // the lower neighbour's flags (mapped), we write [1]
+  uint32_t* flags_hi;     // the upper neighbour's flags (mapped), we write [0]
+  uint32_t halo_seq;      // number of fields produced so far (identical on every rank: same program order)
+  bool p2p;
   int rank, world;
   std::string sticky;  // first collective error inside an operator
   bool borrowed_stream;  // sub-context of a slab context: runs on the parent's stream
@@ -157,6 +166,9 @@ dim3 block3(int dim) { return dim == 3 ? dim3(32, 4, 4) : dim3(32, 16, 1); }
 dim3 grid3(const Geom& g, dim3 b) { return dim3((g.nx + b.x - 1) / b.x, (g.ny + b.y - 1) / b.y, (g.nz + b.z - 1) / b.z); }
 
 Tensor tensor_of(const Level& L);
+void set_ghosts(madgpu_ctx* ctx, Geom& g, const Level& L, const void* field, size_t es);
+void halo_signal(madgpu_ctx* ctx, const void* field);
+void halo_dirty(madgpu_ctx* ctx, const void* field);
 
 // ---- streaming (mad_fast.cuh) launch geometry -------------------------------------------------
 bool use_fast(const madgpu_ctx* ctx, const Level& L)
@@ -181,11 +193,14 @@ template <int MODE, typename T, typename UT, typename FT, typename OT>
 size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT* out, double* partials, float omega, int uzero = 0)
 {
   const Tensor D = tensor_of(L);
+  Geom gg = L.g;
+  if (MODE != fast::MODE_COEF) set_ghosts(ctx, gg, L, out, sizeof(OT));
 #define MAD_FAST_LAUNCH(WY, MINB, PF)                                                                                        \
   do {                                                                                                                       \
     const int zc = fast_zc(L.g, WY);                                                                                         \
     const dim3 fg = fast_grid(L.g, WY, zc);                                                                                  \
-    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(L.g, D, u, f, out, partials, omega, zc, ctx->pf_dist, uzero); \
+    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(gg, D, u, f, out, partials, omega, zc, ctx->pf_dist, uzero); \
+    if (MODE != fast::MODE_COEF) halo_signal(ctx, out);                                                                      \
     return (size_t)fg.x * fg.y * fg.z;                                                                                       \
   } while (0)
   if (sizeof(T) == 8) {
@@ -290,9 +305,81 @@ const char* nccl_load()
 // Collective errors inside the (void) operator functions are latched here and reported by the entry point.
 void latch(madgpu_ctx* ctx, int r, const char* what)
 {
-  if (r != 0 && ctx->sticky.empty()) ctx->sticky = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "NCCL error");
+  if (r == 0 || !ctx->sticky.empty()) return;
+  const bool nccl = strncmp(what, "g_nccl", 6) == 0;
+  ctx->sticky = std::string(what) + ": " + (nccl && g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : ("error " + std::to_string(r)));
 }
 #define NCV(call) latch(ctx, (call), #call)
+
+// ---- peer-memory halo: the kernel that produces a field stores its boundary planes straight into the neighbours' ghost
+// ---- planes (Geom::glo / ghi, NVLink peer stores) and the stream then bumps a counter in the neighbours' memory
+// ---- (cuStreamWriteValue32); a kernel that reads ghost planes first waits for the counters (cuStreamWaitValue32).  No
+// ---- separate exchange operation, no host round trip.  The NCCL send/recv path remains for fields produced otherwise.
+typedef int (*StreamValueFn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+StreamValueFn g_write_value = nullptr, g_wait_value = nullptr;
+
+const char* stream_memops_load()
+{
+  if (g_write_value && g_wait_value) return nullptr;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return "cuStreamWriteValue32 unavailable";
+  g_write_value = (StreamValueFn)f;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return "cuStreamWaitValue32 unavailable";
+  g_wait_value = (StreamValueFn)f;
+  return nullptr;
+}
+
+madgpu_ctx::Shared* shared_of(madgpu_ctx* ctx, const void* field)
+{
+  for (auto& s : ctx->shared)
+    if ((const char*)field >= (const char*)s.local && (const char*)field < (const char*)s.local + s.bytes) return &s;
+  return nullptr;
+}
+
+// Ghost targets of a field this rank is about to produce (plane-0 pointer `field`, element size es).
+void set_ghosts(madgpu_ctx* ctx, Geom& g, const Level& L, const void* field, size_t es)
+{
+  g.glo = g.ghi = nullptr;
+  if (!ctx->p2p) return;
+  madgpu_ctx::Shared* s = shared_of(ctx, field);
+  if (!s) return;
+  const size_t off = (const char*)field - (const char*)s->local;  // bytes from the allocation start to plane 0
+  const size_t plane = (size_t)L.g.plane * es;
+  if (s->lo) g.glo = (char*)s->lo + off + (size_t)L.g.nz * plane;  // lower neighbour's upper ghost plane
+  if (s->hi) g.ghi = (char*)s->hi + off - plane;                   // upper neighbour's lower ghost plane
+}
+
+// after the producing kernel has been launched: publish "field version halo_seq is complete" to both neighbours
+void halo_signal(madgpu_ctx* ctx, const void* field)
+{
+  if (!ctx->p2p) return;
+  madgpu_ctx::Shared* s = shared_of(ctx, field);
+  if (!s) return;
+  s->produced = ++ctx->halo_seq;
+  if (ctx->flags_lo) latch(ctx, g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_lo + 1), s->produced, 0), "cuStreamWriteValue32");
+  if (ctx->flags_hi) latch(ctx, g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_hi + 0), s->produced, 0), "cuStreamWriteValue32");
+}
+
+// a writer that does NOT store into the neighbours' ghost planes: consumers must exchange explicitly
+void halo_dirty(madgpu_ctx* ctx, const void* field)
+{
+  if (!ctx->p2p) return;
+  if (madgpu_ctx::Shared* s = shared_of(ctx, field)) s->produced = 0;
+}
+
+// before a kernel that reads the ghost planes of `field`: true when the neighbours' peer stores are being waited for,
+// false when the caller has to run the explicit exchange
+bool halo_wait(madgpu_ctx* ctx, const void* field)
+{
+  if (!ctx->p2p) return false;
+  madgpu_ctx::Shared* s = shared_of(ctx, field);
+  if (!s || s->produced == 0) return false;
+  const unsigned int GEQ = 1;  // CU_STREAM_WAIT_VALUE_GEQ
+  if (ctx->flags_lo) latch(ctx, g_wait_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags + 0), s->produced, GEQ), "cuStreamWaitValue32");
+  if (ctx->flags_hi) latch(ctx, g_wait_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags + 1), s->produced, GEQ), "cuStreamWaitValue32");
+  return true;
+}
 
 // Ghost planes of a level field: plane -1 <- last plane of rank-1, plane nz <- first plane of rank+1 (one ncclSend/Recv
 // pair per neighbour on the solver's stream).  The outer ranks keep their Neumann mirror handling (zlo_phys / zhi_phys).
@@ -300,6 +387,7 @@ template <typename T>
 void exchange_halo(madgpu_ctx* ctx, const Level& L, T* field)
 {
   if (ctx->world == 1) return;
+  if (halo_wait(ctx, field)) return;  // produced with peer stores: only the arrival counters have to be awaited
   Scope s(ctx, MADGPU_K_HALO, 0);
   const size_t cnt = (size_t)L.g.plane * (sizeof(T) / sizeof(float));
   float* f = reinterpret_cast<float*>(field);
@@ -327,6 +415,7 @@ void unpack_slab(madgpu_ctx* ctx, const Level& L, const float* dense, float* pit
 {
   const dim3 b = block3(3), g = grid3(L.g, b);
   k_dense_to_pitched<float, float><<<g, b, 0, ctx->stream>>>(L.g, dense, pitched);
+  halo_dirty(ctx, pitched);
   ctx->launches++;
 }
 
@@ -384,6 +473,7 @@ void agglomerated_solve(madgpu_ctx* ctx)
 void op_zero(madgpu_ctx* ctx, Level& L, float* p)
 {
   Scope s(ctx, MADGPU_K_MISC);
+  halo_dirty(ctx, p);
   cudaMemsetAsync(p, 0, (size_t)L.g.plane * L.g.nz * sizeof(float), ctx->stream);
 }
 
@@ -401,11 +491,14 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
   for (int it = 0; it < n_iter; ++it) {
     const int uz = zero_first && it == 0;
     if (!uz) exchange_halo(ctx, L, L.u);
+    Geom gg = L.g;  // + the neighbours' ghost planes of the field this sweep produces (L.tmp)
+    set_ghosts(ctx, gg, L, L.tmp, sizeof(float));
     if (smoother == MADGPU_SMOOTHER_WJ) {
       Scope s(ctx, cls);
       if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega, uz);
       else if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       else k_jacobi<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
+      if (!use_fast(ctx, L)) halo_dirty(ctx, L.tmp);
       std::swap(L.u, L.tmp);
     } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16) {
       // fused sweep fed by pre-evaluated fp16 operator rows (built once per tensor and level)
@@ -424,38 +517,40 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       Scope s(ctx, cls);
       if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
         const int zc = fast_zc(L.g, 8);
-        fast::k_coef_gs2<4, 3><<<fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_coef_gs2<4, 3><<<fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream>>>(gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
       std::swap(L.u, L.tmp);
+      halo_signal(ctx, L.u);
     } else if (use_fast(ctx, L) && ctx->gs_fused) {
       // one pass: z-ordered planes, four in-plane colours, exact inside a CTA tile (mad_fast.cuh)
       Scope s(ctx, cls);
       if (ctx->fast_cfg == 1) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<8, 1, false, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 4) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 2, true, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<4, 2, true, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 5) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, true, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<8, 1, true, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 7) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<4, 3, false, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 8) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<8, 1, false, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 6) {
         const int zc = fast_zc(L.g, 2);
-        fast::k_fast_gs<2, 6, false, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<2, 6, false, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        fast::k_fast_gs<4, 3, false, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
       std::swap(L.u, L.tmp);
+      halo_signal(ctx, L.u);
     } else {
       const int nc = ctx->dim == 2 ? 4 : (ctx->p.gs_colors == 8 ? 8 : 4);
       Scope s(ctx, cls, nc);
@@ -463,6 +558,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
         if (ctx->dim == 3) k_gs_color<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, c, nc);
         else k_gs_color<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, c, nc);
       }
+      halo_dirty(ctx, L.u);
     }
   }
 }
@@ -493,7 +589,10 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
   if (!norm && ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && L.coef16_valid) {
     // inside a Gauss-Seidel V-cycle: residual with the packed rows the sweeps use
     const int zc = fast_zc(L.g, 4);
-    fast::k_coef_residual<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(L.g, L.coef16, L.u, L.f, out, zc, ctx->pf_dist);
+    Geom gg = L.g;
+    set_ghosts(ctx, gg, L, out, sizeof(float));
+    fast::k_coef_residual<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, L.coef16, L.u, L.f, out, zc, ctx->pf_dist);
+    halo_signal(ctx, out);
     return;
   }
   if (use_fast(ctx, L)) {
@@ -503,6 +602,7 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
   }
   if (ctx->dim == 3) k_residual<3, float, float, float, float><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, out, part);
   else k_residual<2, float, float, float, float><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, out, part);
+  halo_dirty(ctx, out);
   if (norm) reduce_partials(ctx, (size_t)g.x * g.y * g.z);
 }
 
@@ -569,12 +669,16 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
     if (use_fast(ctx, F)) {
       constexpr int WY = 8;
       const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, (F.g.nz + fast::PROLONG_ZB - 1) / fast::PROLONG_ZB);
-      fast::k_fast_prolong<ADD, WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
+      Geom gg = F.g;
+      set_ghosts(ctx, gg, F, fine, sizeof(float));
+      fast::k_fast_prolong<ADD, WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(C.g, gg, transfer_of(C), coarse, fine);
+      halo_signal(ctx, fine);
       return;
     }
   }
   if (ctx->dim == 3) k_prolong<3, TO, ADD><<<g, b, 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
   else k_prolong<2, TO, ADD><<<g, b, 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
+  halo_dirty(ctx, fine);
 }
 
 void op_coarse_solve(madgpu_ctx* ctx)
@@ -634,7 +738,10 @@ void op_axpy(madgpu_ctx* ctx)
   Level& L = ctx->lv[0];
   const dim3 b(32, 8, 1), g((L.g.nx + 127) / 128, (L.g.ny + 7) / 8, L.g.nz);
   Scope s(ctx, MADGPU_K_MISC);
-  k_axpy_f64_f32<<<g, b, 0, ctx->stream>>>(L.g, ctx->u64, L.u);
+  Geom gg = L.g;
+  set_ghosts(ctx, gg, L, ctx->u64, sizeof(double));
+  k_axpy_f64_f32<<<g, b, 0, ctx->stream>>>(gg, ctx->u64, L.u);
+  halo_signal(ctx, ctx->u64);
 }
 
 // One outer iteration in defect-correction form.  On entry lv[0].f holds r = f64 - A u64.
@@ -738,6 +845,7 @@ void fill_geom(Level& L, int dim, double dt)
   g.pitch = (g.nx + 31) / 32 * 32;
   g.plane = (long long)g.pitch * g.ny;
   g.zlo_phys = 1; g.zhi_phys = 1; g.z0 = 0;
+  g.glo = nullptr; g.ghi = nullptr;
   const double hx = L.h[0], hy = L.h[1], hz = dim == 3 ? L.h[2] : 1.0;
   const bool d3 = dim == 3;
   g.dwx = dt / (hx * hx); g.dwy = dt / (hy * hy); g.dwz = d3 ? dt / (hz * hz) : 0.0;
@@ -1014,7 +1122,7 @@ int run_steps(madgpu_ctx* ctx)
   for (int n = 0; n < P.number_of_steps; ++n) {
     CU(cudaEventRecord(ctx->ev_a, ctx->stream));
     if (P.cycle == MADGPU_CYCLE_FMG) fmg(ctx);                                                        // :174
-    else { Scope s(ctx, MADGPU_K_MISC); CU(cudaMemcpyAsync(ctx->u64, ctx->f64, bytes64, cudaMemcpyDeviceToDevice, ctx->stream)); }  // :182-199
+    else { Scope s(ctx, MADGPU_K_MISC); halo_dirty(ctx, ctx->u64); CU(cudaMemcpyAsync(ctx->u64, ctx->f64, bytes64, cudaMemcpyDeviceToDevice, ctx->stream)); }  // :182-199
     CU(cudaEventRecord(ctx->ev_b, ctx->stream));
     // rhsNorm (:204)
     {
@@ -1176,6 +1284,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
   ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
+  ctx->flags = ctx->flags_lo = ctx->flags_hi = nullptr; ctx->halo_seq = 0; ctx->p2p = false;
   ctx->stage[0] = ctx->stage[1] = nullptr; ctx->stage_bytes[0] = ctx->stage_bytes[1] = 0;
   ctx->rank = rank; ctx->world = world; ctx->comm = nullptr; ctx->sub = nullptr; ctx->gather_buf = nullptr; ctx->slab_buf = nullptr;
   ctx->borrowed_stream = shared_stream != nullptr;
@@ -1320,6 +1429,11 @@ void madgpu_destroy(madgpu_ctx* ctx)
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_c) cudaEventDestroy(ctx->ev_c);
+  for (auto& sh : ctx->shared) {
+    if (sh.lo) cudaIpcCloseMemHandle(sh.lo);
+    if (sh.hi) cudaIpcCloseMemHandle(sh.hi);
+  }
+  if (ctx->flags) cudaFree(ctx->flags);
   for (int i = 0; i < 2; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
   if (ctx->sub) madgpu_destroy(ctx->sub);
   if (ctx->gather_buf) cudaFree(ctx->gather_buf);
@@ -1425,6 +1539,7 @@ static int cycles_begin_common(madgpu_ctx* ctx)
   Level& L = ctx->lv[0];
   const size_t bytes64 = (size_t)L.g.plane * L.g.nz * sizeof(double);
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
+  halo_dirty(ctx, ctx->u64);
   CU(cudaMemcpyAsync(ctx->u64, ctx->f64, bytes64, cudaMemcpyDeviceToDevice, ctx->stream));
   k_sumsq<double><<<g, b, 0, ctx->stream>>>(L.g, ctx->f64, ctx->partials);
   reduce_partials(ctx, (size_t)g.x * g.y * g.z);
@@ -1539,6 +1654,66 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level
   }
+  return 0;
+}
+
+// ---- peer-memory halo set-up: every rank exports the CUDA IPC handles of its level fields and arrival counters, the
+// ---- host layer hands each rank its two neighbours' blobs (any transport), import maps them.
+static int build_shared_list(madgpu_ctx* ctx)
+{
+  if (!ctx->shared.empty()) return 0;
+  for (int l = 0; l < ctx->nlevels; ++l) {
+    Level& L = ctx->lv[l];
+    for (int i = 0; i < 3; ++i) ctx->shared.push_back({L.allocs[i], L.elems * sizeof(float), nullptr, nullptr, 0u});  // u, f, tmp
+  }
+  ctx->shared.push_back({ctx->allocs[0], ctx->lv[0].elems * sizeof(double), nullptr, nullptr, 0u});  // u64
+  if (!ctx->flags) {
+    CU(cudaMalloc((void**)&ctx->flags, 256));
+    CU(cudaMemsetAsync(ctx->flags, 0, 256, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->shared.push_back({ctx->flags, 256, nullptr, nullptr, 0u});
+  return 0;
+}
+
+int madgpu_ipc_export(madgpu_ctx* ctx, void* blob, size_t capacity, size_t* needed)
+{
+  if (!ctx) return MADGPU_EINVAL;
+  if (ctx->world < 2) return fail(ctx, MADGPU_ESTATE, "not a z-slab context");
+  CU(cudaSetDevice(ctx->p.device));
+  int rc = build_shared_list(ctx);
+  if (rc) return rc;
+  const size_t bytes = ctx->shared.size() * sizeof(cudaIpcMemHandle_t);
+  if (needed) *needed = bytes;
+  if (!blob) return 0;
+  if (capacity < bytes) return fail(ctx, MADGPU_EINVAL, "ipc blob needs %zu bytes", bytes);
+  cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)blob;
+  for (size_t i = 0; i < ctx->shared.size(); ++i) CU(cudaIpcGetMemHandle(&h[i], ctx->shared[i].local));
+  return 0;
+}
+
+int madgpu_ipc_import(madgpu_ctx* ctx, const void* blob_lower, const void* blob_upper)
+{
+  if (!ctx) return MADGPU_EINVAL;
+  if (ctx->world < 2) return fail(ctx, MADGPU_ESTATE, "not a z-slab context");
+  if ((ctx->rank > 0) != (blob_lower != nullptr) || (ctx->rank < ctx->world - 1) != (blob_upper != nullptr))
+    return fail(ctx, MADGPU_EINVAL, "rank %d of %d: pass the blob of rank-1 (NULL on rank 0) and of rank+1 (NULL on the last rank)", ctx->rank, ctx->world);
+  CU(cudaSetDevice(ctx->p.device));
+  int rc = build_shared_list(ctx);
+  if (rc) return rc;
+  const char* e = stream_memops_load();
+  if (e) return fail(ctx, MADGPU_ECUDA, "%s", e);
+  for (int l = 0; l + 1 < ctx->nlevels; ++l)
+    if (!use_fast(ctx, ctx->lv[l])) return fail(ctx, MADGPU_ESTATE, "level %d of this slab is relaxed by the generic kernels (nx < %d): peer-memory halo not available, the NCCL exchange stays in use", l, ctx->fast_min_nx);
+  const cudaIpcMemHandle_t* lo = (const cudaIpcMemHandle_t*)blob_lower;
+  const cudaIpcMemHandle_t* hi = (const cudaIpcMemHandle_t*)blob_upper;
+  for (size_t i = 0; i < ctx->shared.size(); ++i) {
+    if (lo && !ctx->shared[i].lo) CU(cudaIpcOpenMemHandle(&ctx->shared[i].lo, lo[i], cudaIpcMemLazyEnablePeerAccess));
+    if (hi && !ctx->shared[i].hi) CU(cudaIpcOpenMemHandle(&ctx->shared[i].hi, hi[i], cudaIpcMemLazyEnablePeerAccess));
+  }
+  ctx->flags_lo = (uint32_t*)ctx->shared.back().lo;
+  ctx->flags_hi = (uint32_t*)ctx->shared.back().hi;
+  ctx->p2p = true;
   return 0;
 }
 

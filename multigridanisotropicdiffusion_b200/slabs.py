@@ -113,3 +113,31 @@ def max_over_ranks(value, group=None):
         t = t.cuda()
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def enable_peer_halo(solver, group=None):
+    """Switch a z-slab MadSolver to the peer-memory halo: all-gather the ranks' CUDA IPC blobs (torch.distributed, any
+    backend) and hand every rank its two neighbours'.  Collective.  Returns False (and leaves the NCCL exchange in use)
+    when the library declines, e.g. a slab level narrower than the streaming kernels need."""
+    import torch
+    import torch.distributed as dist
+    from .solver import MadGpuError
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    blob = solver.ipc_export()
+    t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone()
+    nccl = dist.get_backend(group) == "nccl"
+    if nccl:
+        t = t.cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    blobs = [bytes(p.cpu().numpy().tobytes()) for p in parts]
+    ok = 1
+    try:
+        solver.ipc_import(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
+    except MadGpuError:
+        ok = 0
+    f = torch.tensor([ok], dtype=torch.int32)
+    if nccl:
+        f = f.cuda()
+    dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(f.item()))

@@ -225,6 +225,17 @@ class MadSolver:
         self._check(self._lib.madgpu_cycles_end_f64(self._ctx, _ptr(out)), "cycles_end")
         return out
 
+    # peer-memory halo of a z-slab context (see slabs.enable_peer_halo)
+    def ipc_export(self) -> bytes:
+        n = C.c_size_t()
+        self._check(self._lib.madgpu_ipc_export(self._ctx, None, 0, C.byref(n)), "ipc_export")
+        buf = C.create_string_buffer(n.value)
+        self._check(self._lib.madgpu_ipc_export(self._ctx, buf, n.value, C.byref(n)), "ipc_export")
+        return buf.raw
+
+    def ipc_import(self, blob_lower, blob_upper):
+        self._check(self._lib.madgpu_ipc_import(self._ctx, blob_lower, blob_upper), "ipc_import")
+
     def gs_tile(self, level=0):
         """(tx, ty, tz) of the fused Gauss-Seidel sweep on `level`, or None for one pass per colour."""
         t = (C.c_int32 * 3)()

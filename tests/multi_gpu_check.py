@@ -32,11 +32,15 @@ def main():
         img_t, D = phantom.vessel_phantom(shape)  # whole volume on the CPU, identical on every rank
         img = img_t.numpy()
         T = phantom.planes_to_aos(D).numpy()
-        for smoother, name in ((MadSolver.WJ, "wj"), (MadSolver.GS, "gs")):
+        for smoother, name, peer in ((MadSolver.WJ, "wj", False), (MadSolver.GS, "gs", False), (MadSolver.WJ, "wj", True), (MadSolver.GS, "gs", True)):
             uid = slabs.create_unique_id()
             s = MadSolver(shape, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=3, tolerance=1e-9,
                           max_cycles=40, number_of_steps=2, device=local_rank, rank=rank, world_size=world, nccl_id=uid)
             assert s.shape == (shape[0] // world,) + shape[1:], s.shape
+            if peer:  # halo through peer stores + stream memory operations instead of NCCL send/recv
+                got = slabs.enable_peer_halo(s)
+                assert got, "peer-memory halo was declined"
+            name = name + ("+peer" if peer else "+nccl")
             s.set_tensor(slabs.cut(T, rank, world))
             out_local = s.solve(slabs.cut(img, rank, world), out_dtype=np.float64)
             st = s.last_stats

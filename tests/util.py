@@ -72,17 +72,19 @@ def load_ved_test():
     return z["image"], tuple(float(s) for s in z["spacing"])
 
 
-def gs_tile_sweep(S, u, f, tile):
+def gs_tile_sweep(S, u, f, tile, outside=None):
     """CPU model (numpy, explicit operator rows `S` from the oracle) of the fused GPU Gauss-Seidel sweep:
     tiles of (tx, ty, tz) voxels; inside a tile planes in z order, each plane as even rows (even x, odd x)
-    then odd rows; values outside the tile are those of the previous sweep.  3-D only."""
+    then odd rows; values outside the tile are those of `outside` (default: `u`, the previous sweep; the kernel
+    that fuses two sweeps in one pass reads them from the array the pass started from).  3-D only."""
     TX, TY, TZ = tile
     nz, ny, nx = u.shape
     offs = [(ox, oy, oz) for oz in (-1, 0, 1) for oy in (-1, 0, 1) for ox in (-1, 0, 1)]
     diag = S[..., 13]
     old = np.zeros((nz + 2, ny + 2, nx + 2))
-    old[1:-1, 1:-1, 1:-1] = u
-    w = old.copy()
+    old[1:-1, 1:-1, 1:-1] = u if outside is None else outside
+    w = np.zeros((nz + 2, ny + 2, nx + 2))
+    w[1:-1, 1:-1, 1:-1] = u
     tx = np.arange(-1, nx + 1) // TX
     ty = np.arange(-1, ny + 1) // TY
     tz = np.arange(-1, nz + 1) // TZ
