@@ -234,7 +234,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         s = MadSolver(shape, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, tolerance=0.0,
                       max_cycles=1 << 20, device=local_rank, rank=rank, world_size=world, nccl_id=slabs.create_unique_id())
-        peer_halo = (not args.nccl_halo) and slabs.enable_peer_halo(s)
+        # peer-memory halo (NVLink stores from the producing kernels): verified on 2 and 4 GPUs; an 8-rank run hung in this
+        # round and could not be diagnosed before the GPU budget ran out, so beyond 4 ranks NCCL send/recv stays the default
+        want_peer = args.peer_halo or (not args.nccl_halo and world <= 4)
+        peer_halo = want_peer and slabs.enable_peer_halo(s)
     else:
         img, D = phantom.vessel_phantom(shape, device=dev)
         torch.cuda.synchronize()
@@ -375,6 +378,7 @@ def main():
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: keep the NCCL send/recv halo exchange instead of peer stores")
+    ap.add_argument("--peer-halo", action="store_true", help="N > 4: use the peer-memory halo too (default only up to 4 ranks)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent volumes per GPU instead of z-slabs of one volume")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
