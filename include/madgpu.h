@@ -131,6 +131,9 @@ int madgpu_create_slab(const madgpu_params *p, const void *nccl_unique_id, madgp
  * step.  NCCL send/recv remains the fallback (tensor set-up, agglomeration level, contexts that do not import). */
 int madgpu_ipc_export(madgpu_ctx *ctx, void *blob, size_t capacity, size_t *needed);
 int madgpu_ipc_import(madgpu_ctx *ctx, const void *blob_lower, const void *blob_upper);
+/* import ends with a handshake with both neighbours and fails (MADGPU_ECUDA) when it does not complete; the ranks must then
+ * agree: if any rank failed, all call madgpu_ipc_disable and the NCCL exchange stays in use. */
+int madgpu_ipc_disable(madgpu_ctx *ctx);
 /* planes [z_begin, z_begin + z_count) of `level` held by this context; global_nz = planes of the whole level.
  * Valid for the levels this context holds (all of them when world_size == 1). */
 int madgpu_slab(const madgpu_ctx *ctx, int32_t level, int32_t *z_begin, int32_t *z_count, int32_t *global_nz);

@@ -64,7 +64,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = [
-    "madgpu_params_default", "madgpu_create", "madgpu_create_slab", "madgpu_nccl_unique_id", "madgpu_slab", "madgpu_ipc_export", "madgpu_ipc_import", "madgpu_destroy", "madgpu_last_error", "madgpu_set_solver",
+    "madgpu_params_default", "madgpu_create", "madgpu_create_slab", "madgpu_nccl_unique_id", "madgpu_slab", "madgpu_ipc_export", "madgpu_ipc_import", "madgpu_ipc_disable", "madgpu_destroy", "madgpu_last_error", "madgpu_set_solver",
     "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_set_tensor_device_f32", "madgpu_solve_cast",
     "madgpu_solve_u8", "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_solve_device_f32",
     "madgpu_cycles_begin_device_f32", "madgpu_cycles_begin_f32", "madgpu_cycles_run",
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     L.madgpu_slab.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.madgpu_ipc_export.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.madgpu_ipc_import.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.madgpu_ipc_disable.argtypes = [vp]
     L.madgpu_num_levels.argtypes = [vp]
     L.madgpu_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(f64), C.POINTER(i32)]
     L.madgpu_op_get_tensor.argtypes = [vp, i32, vp]

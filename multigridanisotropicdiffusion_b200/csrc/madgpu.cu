@@ -1713,7 +1713,37 @@ int madgpu_ipc_import(madgpu_ctx* ctx, const void* blob_lower, const void* blob_
   }
   ctx->flags_lo = (uint32_t*)ctx->shared.back().lo;
   ctx->flags_hi = (uint32_t*)ctx->shared.back().hi;
+  // Handshake before anything relies on the mechanism: a stream write into each neighbour's counters block (slots 2 / 3,
+  // apart from the arrival counters) and a bounded host-side poll for theirs.  A driver that refuses stream memory
+  // operations on a peer mapping, or a pair of GPUs without a working peer path, must make this call fail -- a missing
+  // signal later would leave the neighbour's stream waiting for ever.
+  const uint32_t magic = 0xA5A50000u + (uint32_t)ctx->world;
+  int wr = 0;
+  if (ctx->flags_lo) wr |= g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_lo + 3), magic, 0);
+  if (ctx->flags_hi) wr |= g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_hi + 2), magic, 0);
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  bool ok = wr == 0 && se == cudaSuccess;
+  const auto t0 = std::chrono::steady_clock::now();
+  while (ok) {
+    uint32_t got[2] = {0, 0};
+    if (cudaMemcpy(got, ctx->flags + 2, sizeof got, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+    if ((!ctx->flags_lo || got[0] == magic) && (!ctx->flags_hi || got[1] == magic)) break;
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 5.0) ok = false;
+  }
+  if (!ok) {
+    cudaGetLastError();
+    return fail(ctx, MADGPU_ECUDA, "peer-memory handshake with the neighbouring ranks failed (stream write rc %d, %s): the NCCL exchange stays in use", wr,
+                cudaGetErrorString(se));
+  }
   ctx->p2p = true;
+  return 0;
+}
+
+int madgpu_ipc_disable(madgpu_ctx* ctx)
+{
+  if (!ctx) return MADGPU_EINVAL;
+  ctx->p2p = false;
+  for (auto& sh : ctx->shared) sh.produced = 0;
   return 0;
 }
 

@@ -140,4 +140,7 @@ def enable_peer_halo(solver, group=None):
     if nccl:
         f = f.cuda()
     dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
-    return bool(int(f.item()))
+    if int(f.item()) == 0:
+        solver.ipc_disable()  # all or none: a rank that imported must not signal neighbours that did not
+        return False
+    return True

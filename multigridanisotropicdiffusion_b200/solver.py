@@ -236,6 +236,9 @@ class MadSolver:
     def ipc_import(self, blob_lower, blob_upper):
         self._check(self._lib.madgpu_ipc_import(self._ctx, blob_lower, blob_upper), "ipc_import")
 
+    def ipc_disable(self):
+        self._check(self._lib.madgpu_ipc_disable(self._ctx), "ipc_disable")
+
     def gs_tile(self, level=0):
         """(tx, ty, tz) of the fused Gauss-Seidel sweep on `level`, or None for one pass per colour."""
         t = (C.c_int32 * 3)()
