@@ -22,8 +22,8 @@ _ip = C.POINTER(C.c_int)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "mad_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "mad_oracle.c"), os.path.join(_HERE, "ved_oracle.c")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
     return _LIB_PATH
 

@@ -208,3 +208,63 @@ def relres_per_cycle(log, smoother_mode=False):
         cur.append(last)
     steps.append(cur)
     return steps
+
+
+# ---- VED filter (itkVEDMultigridImageFilter.{h,hxx} compiled unmodified; Hessian filter and eigen-solver underneath are
+# ---- the stand-ins of oracle/shim/mini_itk_ved.h, i.e. oracle/ved_oracle.c's vo_hessian / vo_eig3) ----
+_ved_ready = False
+
+
+def _ved_lib():
+    global _ved_ready
+    L = lib()
+    if not _ved_ready:
+        L.mrv_vesselness.restype = C.c_double
+        L.mrv_vesselness.argtypes = [_dp, C.c_double, C.c_double, C.c_double]
+        L.mrv_tensor_from_hessians.argtypes = [_ip, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.mrv_filter.argtypes = [C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                 C.c_int, _dp, _dp]
+        _ved_ready = True
+    return L
+
+
+def ved_available() -> bool:
+    return available() and hasattr(lib(), "mrv_filter")
+
+
+def ved_vesselness(e_sorted_by_magnitude, alpha=0.5, beta=0.5, gamma=5.0) -> float:
+    """VEDMultigridImageFilter::VesselnessFunction"""
+    e = np.ascontiguousarray(e_sorted_by_magnitude, dtype=np.float64)
+    return float(_ved_lib().mrv_vesselness(_d(e), alpha, beta, gamma))
+
+
+def ved_tensor_from_hessians(hessians, spacing_xyz, alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=5.0, sensitivity=10.0):
+    """UpdateVesselness once per Hessian (list of (nz, ny, nx, 6) arrays), then GenerateDiffusionTensor.
+    Returns dict(response, eigenvalues, eigenvectors, tensor)."""
+    hs = np.ascontiguousarray(np.stack([np.asarray(h, dtype=np.float64) for h in hessians]))
+    shape = hs.shape[1:4]
+    p = (C.c_double * 6)(alpha, beta, gamma, epsilon, omega, sensitivity)
+    out = dict(response=np.empty(shape), eigenvalues=np.empty(shape + (3,)), eigenvectors=np.empty(shape + (3, 3)),
+               tensor=np.empty(shape + (6,)))
+    rc = _ved_lib().mrv_tensor_from_hessians(_i3(_xyz(shape)), (C.c_double * 3)(*spacing_xyz), _d(hs), hs.shape[0], p, _d(out["response"]),
+                                             _d(out["eigenvalues"]), _d(out["eigenvectors"]), _d(out["tensor"]))
+    if rc:
+        raise RuntimeError(f"mrv_tensor_from_hessians failed: {rc}")
+    return out
+
+
+def run_ved_filter(image, spacing_xyz, scales, alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=5.0, sensitivity=10.0, iterations=1,
+                   diffusion_iterations=5, smoother=0, cycle=0, time_step=0.1, tolerance=1e-6, iterations_per_grid=2, pixel="double"):
+    """itk::VEDMultigridImageFilter<Image<pixel,3>, Image<pixel,3>, smoother>::Update(), driven like test/itkVEDTest_GS.cxx.
+    Returns (output as float64, diffusion tensor of the last outer iteration)."""
+    img = np.ascontiguousarray(image, dtype=np.float64)
+    out = np.empty_like(img)
+    T = np.empty(img.shape + (6,))
+    p = (C.c_double * 6)(alpha, beta, gamma, epsilon, omega, sensitivity)
+    sc = (C.c_double * len(scales))(*scales)
+    rc = _ved_lib().mrv_filter(_PIXEL[pixel], int(smoother), _i3(_xyz(img.shape)), (C.c_double * 3)(*spacing_xyz), _d(img), p, sc, len(scales),
+                               int(iterations), int(diffusion_iterations), int(cycle), float(time_step), float(tolerance),
+                               int(iterations_per_grid), _d(out), _d(T))
+    if rc:
+        raise RuntimeError(f"mrv_filter failed: {rc}")
+    return out, T
