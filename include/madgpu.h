@@ -183,6 +183,11 @@ int madgpu_cycles_run(madgpu_ctx *ctx, int32_t n, double *relres, float *device_
 int madgpu_cycles_end_device_f32(madgpu_ctx *ctx, float *d_out);
 int madgpu_cycles_end_f64(madgpu_ctx *ctx, double *out);
 
+/* The current iterate (the result of the last solve / cycles_run) cast to a HOST buffer of pixel type out_type
+ * (MADGPU_PIX_*): the output cast of GenerateData (…Filter.hxx:267-284) for callers that drove the solve with device
+ * buffers (madgpu_solve_device_f32, madved_run) and want the fp64 iterate cast once, not via fp32. */
+int madgpu_fetch_output(madgpu_ctx *ctx, int32_t out_type, void *out);
+
 /* relative residual after every cycle of the last solve: hist[step * max_cycles + cycle] */
 int madgpu_get_relres_history(const madgpu_ctx *ctx, double *hist, int32_t capacity);
 

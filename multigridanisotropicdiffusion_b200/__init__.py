@@ -8,6 +8,7 @@ does not load CUDA; the first solver does, and it raises if the library or the G
 from .filter import (MultigridAnisotropicDiffusionImageFilter, MultigridGaussSeidelSmoother,
                      MultigridWeightedJacobiSmoother, VEDMultigridImageFilter)
 from .solver import MadGpuError, MadSolver
+from .ved import MadVed
 
 __all__ = ["MultigridAnisotropicDiffusionImageFilter", "VEDMultigridImageFilter", "MultigridGaussSeidelSmoother",
-           "MultigridWeightedJacobiSmoother", "MadSolver", "MadGpuError"]
+           "MultigridWeightedJacobiSmoother", "MadSolver", "MadVed", "MadGpuError"]

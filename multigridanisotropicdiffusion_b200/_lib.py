@@ -63,6 +63,35 @@ class Stats(C.Structure):
     ]
 
 
+class VedParams(C.Structure):  # madved_params, include/madved.h
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("size", C.c_int32 * 3),
+        ("spacing", C.c_double * 3),
+        ("alpha", C.c_double),
+        ("beta", C.c_double),
+        ("gamma", C.c_double),
+        ("epsilon", C.c_double),
+        ("omega", C.c_double),
+        ("sensitivity", C.c_double),
+        ("device", C.c_int32),
+        ("reserved", C.c_int32 * 7),
+    ]
+
+
+class VedStats(C.Structure):  # madved_stats
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("scales", C.c_int32),
+        ("hessian_ms", C.c_double),
+        ("vesselness_ms", C.c_double),
+        ("h2d_ms", C.c_double),
+        ("d2h_ms", C.c_double),
+        ("diffusion_ms", C.c_double),
+        ("kernel_launches", C.c_int64),
+    ]
+
+
 EXPORTS = [
     "madgpu_params_default", "madgpu_create", "madgpu_create_slab", "madgpu_nccl_unique_id", "madgpu_slab", "madgpu_ipc_export", "madgpu_ipc_import", "madgpu_ipc_disable", "madgpu_destroy", "madgpu_last_error", "madgpu_set_solver",
     "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_set_tensor_device_f32", "madgpu_solve_cast",
@@ -71,7 +100,12 @@ EXPORTS = [
     "madgpu_cycles_end_device_f32", "madgpu_cycles_end_f64", "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info", "madgpu_gs_tile",
     "madgpu_op_get_tensor", "madgpu_op_assemble", "madgpu_op_smooth", "madgpu_op_residual",
     "madgpu_op_residual_f64", "madgpu_op_restrict", "madgpu_op_prolong", "madgpu_op_coarse_solve",
-    "madgpu_op_vcycle",
+    "madgpu_op_vcycle", "madgpu_fetch_output",
+    # include/madved.h
+    "madved_params_default", "madved_create", "madved_destroy", "madved_last_error", "madved_set_params", "madved_set_image",
+    "madved_set_image_device_f32", "madved_image_device", "madved_begin", "madved_hessian", "madved_update_vesselness",
+    "madved_update_vesselness_host_f64", "madved_add_scale", "madved_tensor_planes", "madved_get_tensor_f64",
+    "madved_get_response_f64", "madved_get_hessian_f64", "madved_get_stats", "madved_run",
 ]
 
 _lib = None
@@ -127,5 +161,28 @@ def load() -> C.CDLL:
     L.madgpu_op_prolong.argtypes = [vp, i32, vp, vp]
     L.madgpu_op_coarse_solve.argtypes = [vp, vp, vp]
     L.madgpu_op_vcycle.argtypes = [vp, i32, vp, vp, vp]
+    L.madgpu_fetch_output.argtypes = [vp, i32, vp]
+    L.madved_params_default.argtypes = [C.POINTER(VedParams)]
+    L.madved_params_default.restype = None
+    L.madved_create.argtypes = [C.POINTER(VedParams), C.POINTER(vp)]
+    L.madved_destroy.argtypes = [vp]
+    L.madved_destroy.restype = None
+    L.madved_last_error.argtypes = [vp]
+    L.madved_last_error.restype = C.c_char_p
+    L.madved_set_params.argtypes = [vp, f64, f64, f64, f64, f64, f64]
+    L.madved_set_image.argtypes = [vp, i32, vp]
+    L.madved_set_image_device_f32.argtypes = [vp, vp]
+    L.madved_image_device.argtypes = [vp, C.POINTER(vp)]
+    L.madved_begin.argtypes = [vp]
+    L.madved_hessian.argtypes = [vp, f64]
+    L.madved_update_vesselness.argtypes = [vp]
+    L.madved_update_vesselness_host_f64.argtypes = [vp, vp]
+    L.madved_add_scale.argtypes = [vp, f64]
+    L.madved_tensor_planes.argtypes = [vp, C.POINTER(vp)]
+    L.madved_get_tensor_f64.argtypes = [vp, vp]
+    L.madved_get_response_f64.argtypes = [vp, vp]
+    L.madved_get_hessian_f64.argtypes = [vp, vp]
+    L.madved_get_stats.argtypes = [vp, C.POINTER(VedStats)]
+    L.madved_run.argtypes = [vp, vp, i32, vp, i32, vp, C.POINTER(f64), i32, i32, C.POINTER(Stats)]
     _lib = L
     return L

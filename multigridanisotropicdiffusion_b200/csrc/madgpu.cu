@@ -1629,6 +1629,25 @@ int madgpu_cycles_end_f64(madgpu_ctx* ctx, double* out)
   return 0;
 }
 
+int madgpu_fetch_output(madgpu_ctx* ctx, int32_t out_type, void* out)
+{
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!out) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  if (out_type < 0 || out_type > 3) return fail(ctx, MADGPU_EINVAL, "bad pixel type");
+  CU(cudaSetDevice(ctx->p.device));
+  Level& L = ctx->lv[0];
+  const size_t nvox = (size_t)L.n[0] * L.n[1] * L.n[2];
+  rc = ensure_stage(ctx, 0, nvox * pix_size(out_type));
+  if (rc) return rc;
+  rc = stage_output(ctx, out_type, ctx->stage[0]);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, ctx->stage[0], nvox * pix_size(out_type), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
 int madgpu_get_relres_history(const madgpu_ctx* ctx, double* hist, int32_t capacity)
 {
   if (!ctx || !hist) return MADGPU_EINVAL;

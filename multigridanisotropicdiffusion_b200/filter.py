@@ -115,9 +115,10 @@ class MultigridAnisotropicDiffusionImageFilter:
 
 
 class VEDMultigridImageFilter:
-    """Diffusion half of itk::VEDMultigridImageFilter: the tensor is an input here (the Hessian /
-    vesselness front-end, VED.hxx:158-378, is outside this path -- see DESIGN.md), DiffusionStep
-    (VED.hxx:381-402) is reproduced with its parameter mapping and MaxCycles=100."""
+    """itk::VEDMultigridImageFilter (/root/reference/include/itkVEDMultigridImageFilter.h:41-170): same setters, defaults
+    (VED.hxx:33-58) and GenerateData flow (VED.hxx:63-155) -- per outer iteration the Hessian at every scale, vesselness,
+    tensor, then DiffusionStep -- all of it on the device (include/madved.h).  A tensor handed in with SetDiffusionTensor
+    (not part of the reference's API) replaces the front-end, which is how the solve path alone is driven."""
 
     VCYCLE, FMG, SMOOTHER = MadSolver.VCYCLE, MadSolver.FMG, MadSolver.SMOOTHER
 
@@ -125,10 +126,14 @@ class VEDMultigridImageFilter:
         self._smoother = smoother
         self._device = device
         # defaults: VED.hxx:33-58
+        self._alpha, self._beta, self._gamma = 0.5, 0.5, 5.0
+        self._epsilon, self._omega, self._sensitivity = 0.01, 5.0, 10.0
+        self._scales = [0.300, 0.482, 0.775, 1.245, 2.000]
+        self._iterations = 1
+        self._diffusion_iterations = 5
         self._cycle = self.VCYCLE
         self._time_step = 0.1
         self._tolerance = 1e-6
-        self._diffusion_iterations = 5
         self._diffusion_iterations_per_grid = 2
         self._verbose = False
         self._tensor = None
@@ -136,19 +141,32 @@ class VEDMultigridImageFilter:
         self._spacing = None
         self._output = None
         self.stats = None
+        self.ved_stats = None
 
+    # VED parameters (VED.h:88-96)
+    def SetAlpha(self, v): self._alpha = float(v)
+    def SetBeta(self, v): self._beta = float(v)
+    def SetGamma(self, v): self._gamma = float(v)
+    def SetEpsilon(self, v): self._epsilon = float(v)
+    def SetOmega(self, v): self._omega = float(v)
+    def SetSensitivity(self, v): self._sensitivity = float(v)
+    def SetScales(self, v): self._scales = [float(s) for s in v]
+    def SetIterations(self, n): self._iterations = int(n)
+    def SetDiffusionIterations(self, n): self._diffusion_iterations = int(n)
+    # MAD parameters (VED.h:99-106)
     def SetCycle(self, c): self._cycle = int(c)
     def SetTimeStep(self, dt): self._time_step = float(dt)
     def SetTolerance(self, t): self._tolerance = float(t)
-    def SetDiffusionIterations(self, n): self._diffusion_iterations = int(n)
     def SetDiffusionIterationsPerGrid(self, n): self._diffusion_iterations_per_grid = int(n)
     def SetVerbose(self, v): self._verbose = bool(v)
     def SetDiffusionTensor(self, t): self._tensor = t
+
     def SetInput(self, image, spacing=None):
         self._input = np.asarray(image)
-        self._spacing = spacing
+        self._spacing = tuple(spacing) if spacing is not None else (1.0,) * self._input.ndim
 
     def DiffusionStep(self, image):
+        """VED.hxx:381-402 with a host tensor (SetDiffusionTensor)."""
         f = MultigridAnisotropicDiffusionImageFilter(self._smoother, self._device)
         f.SetVerbose(self._verbose)
         f.SetDiffusionTensor(self._tensor)
@@ -166,7 +184,28 @@ class VEDMultigridImageFilter:
         return out
 
     def Update(self):
-        self._output = self.DiffusionStep(self._input)
+        if self._input is None:
+            raise MadGpuError("no input image")
+        if self._tensor is not None:
+            self._output = self.DiffusionStep(self._input)
+            return self
+        from .ved import MadVed
+        shape = self._input.shape
+        # DiffusionStep's parameter mapping (VED.hxx:386-397)
+        solver = MadSolver(shape, self._spacing, time_step=self._time_step, smoother=_smoother_tag(self._smoother),
+                           iterations_per_grid=self._diffusion_iterations_per_grid, cycle=self._cycle, tolerance=self._tolerance,
+                           max_cycles=100, number_of_steps=self._diffusion_iterations, verbose=self._verbose, device=self._device)
+        try:
+            ved = MadVed(shape, self._spacing, self._alpha, self._beta, self._gamma, self._epsilon, self._omega, self._sensitivity,
+                         device=self._device)
+            try:
+                self._output = ved.run(solver, self._input, self._scales, self._iterations)
+                self.ved_stats = ved.stats()
+                self.stats = solver.last_stats
+            finally:
+                ved.close()
+        finally:
+            solver.close()
         return self
 
     def GetOutput(self):

@@ -69,3 +69,23 @@ def test_reference_ved_diffusion_step():
     o = O.Oracle(vol.shape, sp, T, 0.1, smoother=0, nu=3)
     out, cyc, hist = o.solve(vol.astype(np.float64), tolerance=1e-10, max_cycles=100, number_of_steps=4)
     _check(out, cyc, hist, g)
+
+
+def test_reference_ved_whole_filter():
+    """test/itkVEDTest_GS.cxx ("v") end to end -- Hessians, vesselness, tensor, DiffusionStep, cast -- against the vectors the
+    reference's own VED filter produced (tests/golden/make_golden_ved.py)."""
+    from oracle import ved as V
+    g = _golden("ref_vedfilter_gs_v")
+    vol, sp = load_ved_test()
+    out, info = V.ved_filter(vol, sp, V.DEFAULT_SCALES, alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=1.5, sensitivity=10.0,
+                             iterations=1, diffusion_iterations=4, smoother=0, cycle=0, time_step=0.1, tolerance=1e-10,
+                             iterations_per_grid=3)
+    sub = int(g["sub"])
+    sl = (slice(None, None, sub),) * 3
+    T = info["tensors"][-1]
+    np.testing.assert_allclose(T[sl], g["tensor_sample"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.stack([_stats(T[..., k]) for k in range(6)]), g["tensor_stats"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(out[sl], g["sample"], rtol=0, atol=1e-9 * np.abs(g["sample"]).max())
+    np.testing.assert_allclose(_stats(out), g["stats"], rtol=1e-10)
+    short = np.trunc(out).astype(np.int16)  # static_cast< short >
+    assert (short != g["out_short"]).mean() < 1e-5 and np.abs(short.astype(int) - g["out_short"].astype(int)).max() <= 1

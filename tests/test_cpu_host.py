@@ -1,5 +1,5 @@
-"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/madgpu.h
-declares, parameter defaults mirror the reference's constructors, and -- there being no CPU fallback --
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/madgpu.h and
+include/madved.h declare, parameter defaults mirror the reference's constructors, and -- there being no CPU fallback --
 every compute entry point fails loudly without a GPU.  No CUDA work is done here."""
 import ctypes as C
 import os
@@ -12,17 +12,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_functions():
-    src = open(os.path.join(ROOT, "include", "madgpu.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(madgpu_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for hdr in ("madgpu.h", "madved.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(mad(?:gpu|ved)_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_declares_the_documented_surface():
     names = _header_functions()
     for must in ("madgpu_create", "madgpu_destroy", "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_solve_u8",
-                 "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_last_error", "madgpu_op_vcycle"):
+                 "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_last_error", "madgpu_op_vcycle",
+                 "madved_create", "madved_hessian", "madved_update_vesselness", "madved_update_vesselness_host_f64", "madved_run"):
         assert must in names
-    assert len(names) >= 30
+    assert len(names) >= 50
 
 
 def test_library_exports_every_declared_symbol():
@@ -45,6 +49,41 @@ def test_defaults_mirror_the_reference_constructor():
     assert p.iterations_per_grid == 2 and p.tolerance == 1e-6 and p.max_cycles == 100 and p.verbose == 0
     assert p.smoother == _lib.SMOOTHER_GS and abs(p.omega - 2.0 / 3.0) < 1e-16
     assert p.world_size == 1 and p.rank == 0
+
+
+def test_ved_defaults_mirror_the_reference_constructor():
+    """itkVEDMultigridImageFilter.hxx:33-58."""
+    from multigridanisotropicdiffusion_b200 import _lib
+    from multigridanisotropicdiffusion_b200 import ved
+    lib = _lib.load()
+    p = _lib.VedParams()
+    lib.madved_params_default(C.byref(p))
+    assert p.struct_size == C.sizeof(_lib.VedParams)
+    assert (p.alpha, p.beta, p.gamma, p.epsilon, p.omega, p.sensitivity) == (0.5, 0.5, 5.0, 0.01, 5.0, 10.0)
+    assert ved.DEFAULT_SCALES == (0.300, 0.482, 0.775, 1.245, 2.000)
+    import multigridanisotropicdiffusion_b200 as M
+    v = M.VEDMultigridImageFilter()
+    assert (v._alpha, v._beta, v._gamma, v._epsilon, v._omega, v._sensitivity) == (0.5, 0.5, 5.0, 0.01, 5.0, 10.0)
+    assert v._scales == [0.300, 0.482, 0.775, 1.245, 2.000] and v._iterations == 1 and v._cycle == v.VCYCLE
+
+
+def test_ved_argument_validation_needs_no_gpu():
+    from multigridanisotropicdiffusion_b200 import _lib
+    lib = _lib.load()
+    p = _lib.VedParams()
+    lib.madved_params_default(C.byref(p))
+    ctx = C.c_void_p()
+    p.size[0], p.size[1], p.size[2] = 16, 16, 3  # lines shorter than 4 samples: the recursive filter refuses them
+    assert lib.madved_create(C.byref(p), C.byref(ctx)) == _lib.EINVAL and not ctx.value
+    assert b"4 samples" in lib.madved_last_error(None)
+    p.size[2] = 16
+    p.spacing[1] = 0.0
+    assert lib.madved_create(C.byref(p), C.byref(ctx)) == _lib.EINVAL
+    p.spacing[1] = 1.0
+    p.struct_size = 8
+    assert lib.madved_create(C.byref(p), C.byref(ctx)) == _lib.EINVAL
+    assert lib.madved_hessian(None, 1.0) == _lib.EINVAL
+    assert lib.madved_run(None, None, 0, None, 0, None, None, 0, 0, None) == _lib.EINVAL
 
 
 def test_filter_defaults_and_setters():
@@ -92,6 +131,12 @@ def test_no_cpu_fallback():
     f.SetDiffusionTensor(np.zeros((16, 16, 3), np.float32))
     with pytest.raises(M.MadGpuError):
         f.Update()
+    with pytest.raises(M.MadGpuError):
+        M.MadVed((16, 16, 16))
+    v = M.VEDMultigridImageFilter()
+    v.SetInput(np.zeros((16, 16, 16), np.int16), (0.3, 0.3, 0.5))
+    with pytest.raises(M.MadGpuError):
+        v.Update()  # whole VED filter: device only
 
 
 def test_product_package_never_imports_the_oracle():
