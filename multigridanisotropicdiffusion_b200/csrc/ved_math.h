@@ -17,6 +17,13 @@
 #else
 #define VED_HD inline
 #endif
+#if defined(__CUDA_ARCH__)  // unroll hints for the device pass only (host compilers warn about the pragma)
+#define VED_UNROLL _Pragma("unroll")
+#define VED_UNROLL4 _Pragma("unroll 4")
+#else
+#define VED_UNROLL
+#define VED_UNROLL4
+#endif
 
 namespace ved
 {
@@ -141,21 +148,21 @@ VED_HD void rg_line(const float* __restrict__ x, long long stride, int n, const 
 {
   RgState s[K];
   const double e0 = (double)x[0];
-#pragma unroll
+VED_UNROLL
   for (int k = 0; k < K; ++k) rg_causal_init(s[k], c[k], e0);
-#pragma unroll 4
+VED_UNROLL4
   for (int i = 0; i < n; ++i) {
     const double xi = (double)x[(long long)i * stride];
-#pragma unroll
+VED_UNROLL
     for (int k = 0; k < K; ++k) out[k][(long long)i * stride] = (float)rg_causal_step(s[k], c[k], xi);
   }
   const double e1 = (double)x[(long long)(n - 1) * stride];
-#pragma unroll
+VED_UNROLL
   for (int k = 0; k < K; ++k) rg_anti_init(s[k], c[k], e1);
-#pragma unroll 4
+VED_UNROLL4
   for (int i = n - 1; i >= 0; --i) {
     const double xi = (double)x[(long long)i * stride];
-#pragma unroll
+VED_UNROLL
     for (int k = 0; k < K; ++k) {
       float* o = out[k] + (long long)i * stride;
       *o = (float)(((double)*o + rg_anti_step(s[k], c[k], xi)) * scale[k]);
