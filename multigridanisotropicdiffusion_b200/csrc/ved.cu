@@ -28,159 +28,12 @@
 #include <vector>
 
 #include "../../include/madved.h"
-#include "ved_math.h"
+#include "ved_kernels.cuh"
 
 namespace
 {
 std::string g_ved_create_error;
 
-template <int K>
-struct RgArgs {
-  ved::RgCoefs c[K];
-  float* out[K];
-  double scale[K];  // applied to causal + anticausal (1 / (spacing_a * spacing_b) on the last pass of a Hessian component)
-};
-
-// ---- recursive Gaussian along y or z ---------------------------------------------------------------------------------
-// line t: first element (t / inner) * outer_stride + (t % inner), n elements `stride` apart.
-//   y pass: inner = nx, outer_stride = nx * ny, stride = nx, lines = nx * nz;   z pass: inner = lines = nx * ny, stride = nx * ny.
-template <int K>
-__global__ void __launch_bounds__(128) k_rg_lines(const float* __restrict__ in, RgArgs<K> a, int n, long long stride, long long inner,
-                                                   long long outer_stride, long long nlines)
-{
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nlines) return;
-  const long long base = (t / inner) * outer_stride + (t % inner);
-  float* out[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) out[k] = a.out[k] + base;
-  ved::rg_line<K>(in + base, stride, n, a.c, out, a.scale);
-}
-
-// ---- recursive Gaussian along x ---------------------------------------------------------------------------------------
-constexpr int RG_ROW_WARPS = 2;  // warps per CTA; (1 + K) tiles of 32 x 33 floats per warp: 33.8 KB of shared memory at K = 3
-
-template <int K>
-__global__ void __launch_bounds__(32 * RG_ROW_WARPS) k_rg_rows(const float* __restrict__ in, RgArgs<K> a, int nx, long long nrows)
-{
-  __shared__ float tin[RG_ROW_WARPS][32][33];
-  __shared__ float tout[RG_ROW_WARPS][K][32][33];
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const long long row0 = ((long long)blockIdx.x * RG_ROW_WARPS + wp) * 32;
-  if (row0 >= nrows) return;  // warp-uniform: the warps of a CTA never synchronise with each other
-  const long long myrow = row0 + lane;
-  const bool mine = myrow < nrows;
-  ved::RgState s[K];
-  const int nchunks = (nx + 31) / 32;
-
-  const double e0 = mine ? (double)in[myrow * nx] : 0.0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) ved::rg_causal_init(s[k], a.c[k], e0);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int c0 = ch * 32, w = min(32, nx - c0);
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const long long row = row0 + r;
-      tin[wp][r][lane] = (row < nrows && lane < w) ? in[row * nx + c0 + lane] : 0.f;
-    }
-    __syncwarp();
-    for (int j = 0; j < w; ++j) {
-      const double xi = (double)tin[wp][lane][j];
-#pragma unroll
-      for (int k = 0; k < K; ++k) tout[wp][k][lane][j] = (float)ved::rg_causal_step(s[k], a.c[k], xi);
-    }
-    __syncwarp();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const long long row = row0 + r;
-      if (row < nrows && lane < w) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) a.out[k][row * nx + c0 + lane] = tout[wp][k][r][lane];
-      }
-    }
-    __syncwarp();
-  }
-
-  const double e1 = mine ? (double)in[myrow * nx + nx - 1] : 0.0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) ved::rg_anti_init(s[k], a.c[k], e1);
-  for (int ch = nchunks - 1; ch >= 0; --ch) {
-    const int c0 = ch * 32, w = min(32, nx - c0);
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const long long row = row0 + r;
-      const bool ok = row < nrows && lane < w;
-      tin[wp][r][lane] = ok ? in[row * nx + c0 + lane] : 0.f;
-#pragma unroll
-      for (int k = 0; k < K; ++k) tout[wp][k][r][lane] = ok ? a.out[k][row * nx + c0 + lane] : 0.f;
-    }
-    __syncwarp();
-    for (int j = w - 1; j >= 0; --j) {
-      const double xi = (double)tin[wp][lane][j];
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        tout[wp][k][lane][j] = (float)(((double)tout[wp][k][lane][j] + ved::rg_anti_step(s[k], a.c[k], xi)) * a.scale[k]);
-    }
-    __syncwarp();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const long long row = row0 + r;
-      if (row < nrows && lane < w) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) a.out[k][row * nx + c0 + lane] = tout[wp][k][r][lane];
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// ---- eigen-system + vesselness + tensor ----------------------------------------------------------------------------------
-struct TensorPlanes {
-  float* p[6];
-};
-struct HessianPlanes {
-  const float* p[6];
-};
-
-// SOA: six fp32 planes of this context (offset 0); otherwise a chunk of the caller's AoS fp64 buffer starting at voxel `first_voxel`
-template <bool SOA>
-__global__ void __launch_bounds__(128) k_ved_update(long long first_voxel, long long count, HessianPlanes hs, const double* __restrict__ aos, int first,
-                                                     ved::Params P, double* __restrict__ response, TensorPlanes T)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const long long v = first_voxel + i;
-  double h[6];
-  if (SOA) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) h[k] = (double)hs.p[k][v];
-  } else {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) h[k] = aos[i * 6 + k];
-  }
-  double resp = first ? 0.0 : response[v];
-  double t[6];
-  if (ved::update_voxel(h, first != 0, P, resp, t)) {
-    response[v] = resp;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) T.p[k][v] = (float)t[k];
-  }
-}
-
-template <typename TI>
-__global__ void k_cast_in(const TI* __restrict__ in, float* __restrict__ out, long long n)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i];
-}
-
-__global__ void k_planes_to_aos_f64(HessianPlanes src, double* __restrict__ out, long long first_voxel, long long count)
-{
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) out[i * 6 + k] = (double)src.p[k][first_voxel + i];
-}
 }  // namespace
 
 struct madved_ctx {
@@ -222,7 +75,11 @@ int vfail(madved_ctx* c, int code, const char* fmt, ...)
                    __LINE__, #call, cudaGetErrorString(e_));                                                       \
   } while (0)
 
-unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+vedk::Volume volume_of(const madved_ctx* ctx)
+{
+  const madved_params& p = ctx->p;
+  return vedk::Volume{p.size[0], p.size[1], p.size[2], {p.spacing[0], p.spacing[1], p.spacing[2]}};
+}
 
 size_t vpix_size(int t) { return t == MADGPU_PIX_U8 ? 1 : t == MADGPU_PIX_I16 ? 2 : t == MADGPU_PIX_F32 ? 4 : 8; }
 
@@ -252,26 +109,6 @@ int timer_end(madved_ctx* ctx, double* acc)
   return 0;
 }
 
-template <int K>
-void launch_rows(madved_ctx* ctx, const float* in, const RgArgs<K>& a)
-{
-  const long long nrows = (long long)ctx->p.size[1] * ctx->p.size[2];
-  const long long warps = (nrows + 31) / 32;
-  k_rg_rows<K><<<blocks_for(warps, RG_ROW_WARPS), 32 * RG_ROW_WARPS, 0, ctx->stream>>>(in, a, ctx->p.size[0], nrows);
-  ctx->st.kernel_launches++;
-}
-
-// axis 1 (y) or 2 (z)
-template <int K>
-void launch_lines(madved_ctx* ctx, int axis, const float* in, const RgArgs<K>& a)
-{
-  const long long nx = ctx->p.size[0], ny = ctx->p.size[1], nz = ctx->p.size[2];
-  const long long nlines = axis == 1 ? nx * nz : nx * ny;
-  const long long inner = axis == 1 ? nx : nx * ny;
-  k_rg_lines<K><<<blocks_for(nlines, 128), 128, 0, ctx->stream>>>(in, a, (int)(axis == 1 ? ny : nz), axis == 1 ? nx : nx * ny, inner, nx * ny, nlines);
-  ctx->st.kernel_launches++;
-}
-
 // ComputeHessian, itkVEDMultigridImageFilter.hxx:158-173 (HessianRecursiveGaussianImageFilter, NormalizeAcrossScale on).
 // Separable: H_ab = (d_a d_b G) * I.  The x pass yields G0x, G1x, G2x of the image in one read; the y pass the six xy products;
 // the z pass the six components, scaled by 1 / (h_a h_b).
@@ -279,48 +116,9 @@ int hessian(madved_ctx* ctx, double sigma)
 {
   if (!ctx->have_image) return vfail(ctx, MADGPU_ESTATE, "no image (madved_set_image first)");
   if (!(sigma > 0.0)) return vfail(ctx, MADGPU_EINVAL, "sigma must be positive");
-  ved::RgCoefs c[3][3];  // [axis][order]
-  for (int ax = 0; ax < 3; ++ax)
-    for (int o = 0; o < 3; ++o) ved::rg_setup(sigma, ctx->p.spacing[ax], o, true, c[ax][o]);
-  float** W = ctx->work;
-  float *G0x = W[0], *G1x = W[1], *G2x = W[2];
-  float *Pxx = W[3], *Pxy = W[4], *Pxz = W[5], *Pyy = W[6], *Pyz = W[7], *Pzz = W[8];
   int rc = timer_begin(ctx);
   if (rc) return rc;
-  {  // x pass
-    RgArgs<3> a;
-    for (int o = 0; o < 3; ++o) { a.c[o] = c[0][o]; a.scale[o] = 1.0; }
-    a.out[0] = G0x; a.out[1] = G1x; a.out[2] = G2x;
-    launch_rows<3>(ctx, ctx->image, a);
-  }
-  {  // y pass
-    RgArgs<3> a3;
-    for (int o = 0; o < 3; ++o) { a3.c[o] = c[1][o]; a3.scale[o] = 1.0; }
-    a3.out[0] = Pzz; a3.out[1] = Pyz; a3.out[2] = Pyy;  // G0x -> G0y, G1y, G2y
-    launch_lines<3>(ctx, 1, G0x, a3);
-    RgArgs<2> a2;
-    for (int o = 0; o < 2; ++o) { a2.c[o] = c[1][o]; a2.scale[o] = 1.0; }
-    a2.out[0] = Pxz; a2.out[1] = Pxy;  // G1x -> G0y, G1y
-    launch_lines<2>(ctx, 1, G1x, a2);
-    RgArgs<1> a1;
-    a1.c[0] = c[1][0]; a1.scale[0] = 1.0;
-    a1.out[0] = Pxx;  // G2x -> G0y
-    launch_lines<1>(ctx, 1, G2x, a1);
-  }
-  {  // z pass; component order (0,0),(0,1),(0,2),(1,1),(1,2),(2,2); the x-pass volumes are free again and take three outputs
-    const double* h = ctx->p.spacing;
-    struct { const float* in; float* out; int order; double factor; } z[6] = {
-        {Pxx, W[0], 0, h[0] * h[0]}, {Pxy, W[1], 0, h[0] * h[1]}, {Pxz, W[2], 1, h[0] * h[2]},
-        {Pyy, W[9], 0, h[1] * h[1]}, {Pyz, W[10], 1, h[1] * h[2]}, {Pzz, W[11], 2, h[2] * h[2]}};
-    for (int k = 0; k < 6; ++k) {
-      RgArgs<1> a;
-      a.c[0] = c[2][z[k].order];
-      a.scale[0] = 1.0 / z[k].factor;
-      a.out[0] = z[k].out;
-      launch_lines<1>(ctx, 2, z[k].in, a);
-      ctx->H[k] = z[k].out;
-    }
-  }
+  ctx->st.kernel_launches += vedk::hessian_passes(ctx->stream, volume_of(ctx), sigma, ctx->image, ctx->work, ctx->H);
   rc = timer_end(ctx, &ctx->st.hessian_ms);
   if (rc) return rc;
   ctx->have_hessian = true;
@@ -330,13 +128,10 @@ int hessian(madved_ctx* ctx, double sigma)
 int update_from_planes(madved_ctx* ctx)
 {
   if (!ctx->have_hessian) return vfail(ctx, MADGPU_ESTATE, "no Hessian (madved_hessian first)");
-  HessianPlanes hs;
-  TensorPlanes T;
-  for (int k = 0; k < 6; ++k) { hs.p[k] = ctx->H[k]; T.p[k] = ctx->T[k]; }
-  ved::Params P = {ctx->p.alpha, ctx->p.beta, ctx->p.gamma, ctx->p.epsilon, ctx->p.omega, ctx->p.sensitivity};
+  const ved::Params P = {ctx->p.alpha, ctx->p.beta, ctx->p.gamma, ctx->p.epsilon, ctx->p.omega, ctx->p.sensitivity};
   int rc = timer_begin(ctx);
   if (rc) return rc;
-  k_ved_update<true><<<blocks_for(ctx->nvox, 128), 128, 0, ctx->stream>>>(0, ctx->nvox, hs, nullptr, ctx->first ? 1 : 0, P, ctx->response, T);
+  vedk::launch_update_planes(ctx->stream, ctx->nvox, ctx->H, ctx->first, P, ctx->response, ctx->T);
   ctx->st.kernel_launches++;
   rc = timer_end(ctx, &ctx->st.vesselness_ms);
   if (rc) return rc;
@@ -355,11 +150,10 @@ int upload_image(madved_ctx* ctx, int type, const void* host)
     int rc = ensure_vstage(ctx, bytes);
     if (rc) return rc;
     VCU(cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    const unsigned bl = blocks_for(ctx->nvox, 256);
     switch (type) {
-      case MADGPU_PIX_U8: k_cast_in<uint8_t><<<bl, 256, 0, ctx->stream>>>((const uint8_t*)ctx->stage, ctx->image, ctx->nvox); break;
-      case MADGPU_PIX_I16: k_cast_in<int16_t><<<bl, 256, 0, ctx->stream>>>((const int16_t*)ctx->stage, ctx->image, ctx->nvox); break;
-      case MADGPU_PIX_F64: k_cast_in<double><<<bl, 256, 0, ctx->stream>>>((const double*)ctx->stage, ctx->image, ctx->nvox); break;
+      case MADGPU_PIX_U8: vedk::launch_cast_in(ctx->stream, (const uint8_t*)ctx->stage, ctx->image, ctx->nvox); break;
+      case MADGPU_PIX_I16: vedk::launch_cast_in(ctx->stream, (const int16_t*)ctx->stage, ctx->image, ctx->nvox); break;
+      case MADGPU_PIX_F64: vedk::launch_cast_in(ctx->stream, (const double*)ctx->stage, ctx->image, ctx->nvox); break;
       default: return vfail(ctx, MADGPU_EINVAL, "bad pixel type %d", type);
     }
     ctx->st.kernel_launches++;
@@ -539,14 +333,11 @@ int madved_update_vesselness_host_f64(madved_ctx* ctx, const double* hessian_aos
   const long long chunk = std::min<long long>(ctx->nvox, 2ll << 20);  // voxels per staging chunk (96 MB)
   int rc = ensure_vstage(ctx, (size_t)chunk * 6 * sizeof(double));
   if (rc) return rc;
-  HessianPlanes hs = {};
-  TensorPlanes T;
-  for (int k = 0; k < 6; ++k) T.p[k] = ctx->T[k];
-  ved::Params P = {ctx->p.alpha, ctx->p.beta, ctx->p.gamma, ctx->p.epsilon, ctx->p.omega, ctx->p.sensitivity};
+  const ved::Params P = {ctx->p.alpha, ctx->p.beta, ctx->p.gamma, ctx->p.epsilon, ctx->p.omega, ctx->p.sensitivity};
   for (long long v0 = 0; v0 < ctx->nvox; v0 += chunk) {
     const long long cnt = std::min(chunk, ctx->nvox - v0);
     VCU(cudaMemcpyAsync(ctx->stage, hessian_aos + v0 * 6, (size_t)cnt * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    k_ved_update<false><<<blocks_for(cnt, 128), 128, 0, ctx->stream>>>(v0, cnt, hs, (const double*)ctx->stage, ctx->first ? 1 : 0, P, ctx->response, T);
+    vedk::launch_update_aos(ctx->stream, v0, cnt, (const double*)ctx->stage, ctx->first, P, ctx->response, ctx->T);
     ctx->st.kernel_launches++;
     VCU(cudaStreamSynchronize(ctx->stream));  // the single staging buffer is reused by the next chunk
   }
@@ -570,11 +361,9 @@ static int planes_to_host_aos(madved_ctx* ctx, const float* const* planes, doubl
   const long long chunk = std::min<long long>(ctx->nvox, 2ll << 20);
   int rc = ensure_vstage(ctx, (size_t)chunk * 6 * sizeof(double));
   if (rc) return rc;
-  HessianPlanes src;
-  for (int k = 0; k < 6; ++k) src.p[k] = planes[k];
   for (long long v0 = 0; v0 < ctx->nvox; v0 += chunk) {
     const long long cnt = std::min(chunk, ctx->nvox - v0);
-    k_planes_to_aos_f64<<<blocks_for(cnt, 256), 256, 0, ctx->stream>>>(src, (double*)ctx->stage, v0, cnt);
+    vedk::launch_planes_to_aos(ctx->stream, planes, (double*)ctx->stage, v0, cnt);
     VCU(cudaMemcpyAsync(out + v0 * 6, ctx->stage, (size_t)cnt * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     VCU(cudaStreamSynchronize(ctx->stream));
   }

@@ -3,10 +3,13 @@
 1. The oracle's restatement of the third-party pieces (oracle/ved_oracle.c: recursive Gaussian, Hessian, eigen-solver) against
    independent implementations: sampled-Gaussian convolution (scipy), polynomial known answers, LAPACK.  This BOUNDS
    restatement errors; it does not pin ITK's filter (parity unpinned, see the header of ved_oracle.c).
-2. The arithmetic the CUDA kernels execute (csrc/ved_math.h), compiled for the host by tests/ved_host_harness.cpp, against
-   the oracle -- coefficient set-up, line recursion with fp32 intermediate storage, the separable Hessian in the kernels'
-   pass order, eigen-solver, vesselness, per-voxel update.  The tolerances found here are the ones tests/test_gpu_ved.py uses.
-No GPU, no compute call into libmadgpu.so.
+2. The source of the CUDA kernels themselves, compiled for the host by tests/ved_host_harness.cpp, against the oracle:
+   csrc/ved_math.h (coefficient set-up, line recursion with fp32 intermediate storage, eigen-solver, vesselness, per-voxel update)
+   and csrc/ved_kernels.cuh -- the unmodified __global__ kernels with their launch geometry and the pass structure of the
+   separable Hessian, run on host threads through tests/cuda_host_shim.h (threadIdx / __shared__ / __syncwarp / launch), so
+   indexing, the shared-memory tile walk of the x pass, ragged edges and buffer reuse are exercised as written.
+   The tolerances found here are the ones tests/test_gpu_ved.py uses.
+No GPU, no compute call into libmadgpu.so; the context / C-ABI / copy layer of ved.cu is what only the GPU tests reach.
 """
 import ctypes as C
 import os
@@ -26,21 +29,27 @@ VED_TEST = dict(alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=1.5, sensiti
 
 @pytest.fixture(scope="module")
 def host():
-    """ved_math.h compiled for the host."""
+    """ved_math.h + ved_kernels.cuh compiled for the host."""
+    csrc = os.path.join(ROOT, "multigridanisotropicdiffusion_b200", "csrc")
     src = os.path.join(ROOT, "tests", "ved_host_harness.cpp")
-    hdr = os.path.join(ROOT, "multigridanisotropicdiffusion_b200", "csrc", "ved_math.h")
+    deps = [src, os.path.join(ROOT, "tests", "cuda_host_shim.h"), os.path.join(csrc, "ved_math.h"), os.path.join(csrc, "ved_kernels.cuh")]
     out = os.path.join(ROOT, "tests", "_build", "libvedhost.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", out, src])
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-o", out, src])
     L = C.CDLL(out)
     L.vh_rg_setup.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _dp]
     L.vh_rg_line.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_double]
     L.vh_hessian.argtypes = [_ip, _dp, C.c_double, _fp, _fp]
+    L.vh_hessian.restype = C.c_int
     L.vh_eig3_top.argtypes = [_dp, _dp, _dp]
     L.vh_vesselness.restype = C.c_double
     L.vh_vesselness.argtypes = [_dp, C.c_double, C.c_double, C.c_double]
-    L.vh_update.argtypes = [C.c_longlong, C.c_int, _fp, _dp, C.c_int, _dp, _dp, _fp]
+    L.vh_update.argtypes = [C.c_longlong, C.c_int, _fp, _dp, C.c_int, _dp, _dp, _fp, C.c_longlong]
+    L.vh_cast_in_i16.argtypes = [C.c_void_p, _fp, C.c_longlong]
+    L.vh_cast_in_u8.argtypes = [C.c_void_p, _fp, C.c_longlong]
+    L.vh_cast_in_f64.argtypes = [C.c_void_p, _fp, C.c_longlong]
+    L.vh_planes_to_aos.argtypes = [_fp, C.c_longlong, _dp, C.c_longlong, C.c_longlong]
     return L
 
 
@@ -184,7 +193,8 @@ def hessians(host):
 
 
 def test_device_hessian_pass_structure_matches_oracle(hessians):
-    """Shared x / y passes, fp32 intermediates, per-component scaling: <= 2e-6 of the component's range at every scale."""
+    """The kernels (k_rg_rows, k_rg_lines) with shared x / y passes, fp32 intermediates, per-component scaling:
+    <= 2e-6 of the component's range at every scale."""
     _, _, ho, hk = hessians
     for s, Ho, Hk in zip(V.DEFAULT_SCALES, ho, hk):
         for k in range(6):
@@ -224,7 +234,7 @@ def test_device_vesselness_matches_oracle(host):
         assert host.vh_vesselness(_d(e), 0.5, 0.5, 5.0) == V.vesselness(e, 0.5, 0.5, 5.0)
 
 
-def _update_all(host, shape, hs, soa, params):
+def _update_all(host, shape, hs, soa, params, chunk=0):
     nvox = int(np.prod(shape))
     resp = np.empty(nvox)
     T = np.empty((6, nvox), dtype=np.float32)
@@ -232,10 +242,10 @@ def _update_all(host, shape, hs, soa, params):
     for i, H in enumerate(hs):
         if soa:
             H = np.ascontiguousarray(H, dtype=np.float32)
-            host.vh_update(nvox, 1, _f(H), None, int(i == 0), _d(p), _d(resp), _f(T))
+            host.vh_update(nvox, 1, _f(H), None, int(i == 0), _d(p), _d(resp), _f(T), nvox)
         else:
             H = np.ascontiguousarray(H, dtype=np.float64)
-            host.vh_update(nvox, 0, None, _d(H), int(i == 0), _d(p), _d(resp), _f(T))
+            host.vh_update(nvox, 0, None, _d(H), int(i == 0), _d(p), _d(resp), _f(T), chunk or nvox)
     return resp.reshape(shape), np.moveaxis(T.reshape((6,) + tuple(shape)), 0, -1)
 
 
@@ -257,7 +267,7 @@ def test_device_update_random_hessians_and_first_scale_rule(host):
     shape = (6, 7, 8)
     hs = [rng.normal(size=shape + (6,)) * s for s in (1.0, 3.0, 0.2)]
     params = [0.5, 0.5, 5.0, 0.01, 5.0, 10.0]
-    resp, T = _update_all(host, shape, hs, False, params)
+    resp, T = _update_all(host, shape, hs, False, params, chunk=100)  # 336 voxels in chunks of 100: ragged last chunk
     To, st = V.ved_tensor(np.zeros(shape), (1, 1, 1), scales=(1, 2, 3), hessians=hs)
     np.testing.assert_allclose(resp, st.response, rtol=1e-12, atol=1e-300)
     np.testing.assert_allclose(T, To, atol=1e-6)
@@ -274,3 +284,33 @@ def test_device_pipeline_fp32_hessians_vs_oracle(host, hessians):
     assert bad.mean() < 5e-3, bad.mean()
     assert rel_l2(T, To) < 2e-3
     np.testing.assert_allclose(resp[~bad], st.response[~bad], rtol=2e-3, atol=1e-9)
+
+
+# shapes: nx a multiple of 32, ragged last tile, nx < 32, minimum line length on every axis, rows not a multiple of 32, one row tile
+@pytest.mark.parametrize("shape,sp", [((6, 7, 64), (1.0, 1.0, 1.0)), ((9, 7, 69), (0.5, 0.4, 0.8)), ((12, 14, 30), (0.3125, 0.3125, 0.5)),
+                                      ((4, 5, 4), (1.0, 1.0, 1.0)), ((5, 13, 97), (0.33, 0.33, 0.33)), ((4, 4, 33), (1.0, 2.0, 0.5))])
+def test_device_hessian_kernels_on_awkward_shapes(host, shape, sp):
+    """Every output voxel is written (the work volumes are poisoned), 10 launches per scale, Hessian within 5e-6 of its range."""
+    img = (100 + 20 * np.random.default_rng(sum(shape)).normal(size=shape)).astype(np.float32)
+    for sigma in (0.3, 1.245):
+        H = np.empty((6,) + shape, dtype=np.float32)
+        launches = host.vh_hessian((C.c_int * 3)(*shape[::-1]), (C.c_double * 3)(*sp), sigma, _f(img), _f(H))
+        assert launches == 10
+        Ho = V.hessian(img.astype(np.float64), sp, sigma)
+        for k in range(6):
+            err = np.abs(H[k] - Ho[..., k]).max() / np.abs(Ho[..., k]).max()
+            assert err < 5e-6, (shape, sigma, k, err)
+
+
+def test_device_cast_and_layout_kernels(host):
+    rng = np.random.default_rng(9)
+    n = 1000  # not a multiple of the block size
+    for name, a in (("i16", rng.integers(-3000, 3000, n).astype(np.int16)), ("u8", rng.integers(0, 255, n).astype(np.uint8)),
+                    ("f64", rng.normal(size=n) * 1e3)):
+        out = np.full(n, np.nan, dtype=np.float32)
+        getattr(host, "vh_cast_in_" + name)(a.ctypes.data_as(C.c_void_p), _f(out), n)
+        np.testing.assert_array_equal(out, a.astype(np.float32))
+    planes = rng.normal(size=(6, n)).astype(np.float32)
+    out = np.full((300, 6), np.nan)
+    host.vh_planes_to_aos(_f(planes), n, _d(out), 650, 300)  # a chunk in the middle
+    np.testing.assert_array_equal(out, planes[:, 650:950].T.astype(np.float64))
