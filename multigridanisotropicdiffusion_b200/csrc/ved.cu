@@ -23,6 +23,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,6 +49,7 @@ struct madved_ctx {
   double* response;
   void* stage;  // host<->device staging, grown on demand
   size_t stage_bytes;
+  long long stage_voxels;  // voxels per staging chunk of the AoS fp64 paths (MADVED_STAGE_VOXELS, default 2 Mi = 96 MB)
   bool first, have_image, have_hessian, have_tensor;
   madved_stats st;
   std::string err;
@@ -236,6 +238,8 @@ int madved_create(const madved_params* p, madved_ctx** out)
   for (auto& t : c->T) t = nullptr;
   for (auto& h : c->H) h = nullptr;
   c->have_image = c->have_hessian = false;
+  c->stage_voxels = 2ll << 20;
+  if (const char* e = getenv("MADVED_STAGE_VOXELS")) c->stage_voxels = std::max(1ll, atoll(e));
   begin(c);
   ctx = c;
   auto bail = [&](cudaError_t e, const char* what) {
@@ -330,7 +334,7 @@ int madved_update_vesselness_host_f64(madved_ctx* ctx, const double* hessian_aos
   if (!ctx) return MADGPU_EINVAL;
   if (!hessian_aos) return vfail(ctx, MADGPU_EINVAL, "null Hessian pointer");
   VCU(cudaSetDevice(ctx->p.device));
-  const long long chunk = std::min<long long>(ctx->nvox, 2ll << 20);  // voxels per staging chunk (96 MB)
+  const long long chunk = std::min<long long>(ctx->nvox, ctx->stage_voxels);
   int rc = ensure_vstage(ctx, (size_t)chunk * 6 * sizeof(double));
   if (rc) return rc;
   const ved::Params P = {ctx->p.alpha, ctx->p.beta, ctx->p.gamma, ctx->p.epsilon, ctx->p.omega, ctx->p.sensitivity};
@@ -358,7 +362,7 @@ int madved_tensor_planes(madved_ctx* ctx, const float** planes)
 
 static int planes_to_host_aos(madved_ctx* ctx, const float* const* planes, double* out)
 {
-  const long long chunk = std::min<long long>(ctx->nvox, 2ll << 20);
+  const long long chunk = std::min<long long>(ctx->nvox, ctx->stage_voxels);
   int rc = ensure_vstage(ctx, (size_t)chunk * 6 * sizeof(double));
   if (rc) return rc;
   for (long long v0 = 0; v0 < ctx->nvox; v0 += chunk) {
