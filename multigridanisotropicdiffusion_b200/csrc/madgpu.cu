@@ -1736,6 +1736,9 @@ int madgpu_ipc_import(madgpu_ctx* ctx, const void* blob_lower, const void* blob_
   // apart from the arrival counters) and a bounded host-side poll for theirs.  A driver that refuses stream memory
   // operations on a peer mapping, or a pair of GPUs without a working peer path, must make this call fail -- a missing
   // signal later would leave the neighbour's stream waiting for ever.
+  const bool dbg = getenv("MADGPU_P2P_DEBUG") != nullptr;  // one line per step on stderr, to locate a rank that stalls or fails
+  if (dbg) fprintf(stderr, "[madgpu p2p] rank %d/%d: %zu allocations mapped from %s%s, starting handshake\n", ctx->rank, ctx->world, ctx->shared.size(),
+                   lo ? "rank-1 " : "", hi ? "rank+1" : "");
   const uint32_t magic = 0xA5A50000u + (uint32_t)ctx->world;
   int wr = 0;
   if (ctx->flags_lo) wr |= g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_lo + 3), magic, 0);
@@ -1749,6 +1752,8 @@ int madgpu_ipc_import(madgpu_ctx* ctx, const void* blob_lower, const void* blob_
     if ((!ctx->flags_lo || got[0] == magic) && (!ctx->flags_hi || got[1] == magic)) break;
     if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) ok = false;  // neighbours open ~20 IPC handles first: allow for the skew
   }
+  if (dbg) fprintf(stderr, "[madgpu p2p] rank %d: handshake %s after %.3f s (stream write rc %d, sync %s)\n", ctx->rank, ok ? "ok" : "FAILED",
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), wr, cudaGetErrorString(se));
   if (!ok) {
     cudaGetLastError();
     return fail(ctx, MADGPU_ECUDA, "peer-memory handshake with the neighbouring ranks failed (stream write rc %d, %s): the NCCL exchange stays in use", wr,
