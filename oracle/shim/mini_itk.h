@@ -254,6 +254,7 @@ public:
   typedef ImageRegion<VDim> RegionType;
   typedef FixedVector<double, VDim> SpacingType;
   typedef FixedVector<double, VDim> PointType;
+  typedef FixedVector<double, VDim * VDim> DirectionType;  // row-major, identity by default
   static const unsigned int ImageDimension = VDim;
 
   itkNewMacro(Self);
@@ -270,6 +271,8 @@ public:
   void SetSpacing(const SpacingType& s) { m_Spacing = s; }
   const PointType& GetOrigin() const { return m_Origin; }
   void SetOrigin(const PointType& o) { m_Origin = o; }
+  const DirectionType& GetDirection() const { return m_Direction; }
+  void SetDirection(const DirectionType& d) { m_Direction = d; }
   TPixel& GetPixel(const IndexType& i) { return m_Buffer[ComputeOffset(i)]; }
   const TPixel& GetPixel(const IndexType& i) const { return m_Buffer[ComputeOffset(i)]; }
   void SetPixel(const IndexType& i, const TPixel& v) { m_Buffer[ComputeOffset(i)] = v; }
@@ -284,18 +287,42 @@ public:
     }
     return o;
   }
-  void Graft(const Self* o) { m_Region = o->m_Region; m_Spacing = o->m_Spacing; m_Origin = o->m_Origin; m_Buffer = o->m_Buffer; }
+  void Graft(const Self* o) { m_Region = o->m_Region; m_Spacing = o->m_Spacing; m_Origin = o->m_Origin; m_Direction = o->m_Direction; m_Buffer = o->m_Buffer; }
 
 protected:
-  Image() { m_Spacing.Fill(1.0); m_Origin.Fill(0.0); }
+  Image()
+  {
+    m_Spacing.Fill(1.0);
+    m_Origin.Fill(0.0);
+    m_Direction.Fill(0.0);
+    for (unsigned int d = 0; d < VDim; ++d) m_Direction[d * VDim + d] = 1.0;
+  }
   virtual ~Image() {}
 
 private:
   RegionType m_Region;
   SpacingType m_Spacing;
   PointType m_Origin;
+  DirectionType m_Direction;
   std::vector<TPixel> m_Buffer;
 };
+
+template <unsigned int D>
+std::ostream& operator<<(std::ostream& os, const ImageRegion<D>& r)
+{
+  os << "ImageRegion: index [";
+  for (unsigned int d = 0; d < D; ++d) os << (d ? ", " : "") << r.GetIndex(d);
+  os << "] size [";
+  for (unsigned int d = 0; d < D; ++d) os << (d ? ", " : "") << r.GetSize(d);
+  return os << "]";
+}
+template <typename TPixel, unsigned int VDim>
+std::ostream& operator<<(std::ostream& os, const Image<TPixel, VDim>& img)
+{
+  os << "Image (stand-in ITK): " << img.GetLargestPossibleRegion() << " spacing [";
+  for (unsigned int d = 0; d < VDim; ++d) os << (d ? ", " : "") << img.GetSpacing()[d];
+  return os << "]";
+}
 template <typename TPixel, unsigned int VDim>
 const unsigned int Image<TPixel, VDim>::ImageDimension;
 
