@@ -148,3 +148,26 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle" not in txt.replace("the oracle", "").replace("CPU oracle", "").lower() or fn == "phantom.py" \
                     or "import oracle" not in txt and "from oracle" not in txt and "libmadoracle" not in txt, fn
                 assert "from oracle" not in txt and "import oracle" not in txt and "libmadoracle" not in txt and "mad_oracle" not in txt, fn
+
+
+def test_cmake_packaging_configures(tmp_path):
+    """CMakeLists.txt (standalone mode): configures with the CUDA language for sm_100a and declares the library, the drop-in test
+    programs and -- where the reference is present -- its nine CTest entries.  MADGPU_TEST_CMAKE_BUILD=1 also builds everything."""
+    import shutil
+    import subprocess
+    if not shutil.which("cmake") or not shutil.which("nvcc"):
+        pytest.skip("cmake / nvcc not available")
+    b = str(tmp_path / "build")
+    r = subprocess.run(["cmake", "-S", ROOT, "-B", b], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    cache = open(os.path.join(b, "CMakeCache.txt")).read()
+    assert "CMAKE_CUDA_COMPILER" in cache
+    r = subprocess.run(["cmake", "--build", b, "--target", "help"], capture_output=True, text=True)
+    assert "madgpu" in r.stdout and "dropin_test" in r.stdout and "ved_dropin_test" in r.stdout
+    if os.path.isdir("/root/reference/test"):
+        assert "ref_tests_dropin" in r.stdout
+        t = subprocess.run(["ctest", "--test-dir", b, "-N"], capture_output=True, text=True).stdout
+        assert "Total Tests: 9" in t and "itkVEDTest_GS_FMG" in t and "itk2DDiffusionTest_WJ_S" in t
+    if os.environ.get("MADGPU_TEST_CMAKE_BUILD") == "1":
+        assert subprocess.run(["cmake", "--build", b, "-j", "4"], capture_output=True, text=True).returncode == 0
+        assert os.path.exists(os.path.join(b, "libmadgpu.so"))
