@@ -16,8 +16,10 @@ level-0 residual-norm stop test and its read-back, exactly one pass of the refer
   roofline: level-0 smoother sweep, 36 B/voxel algorithmic (u, f, u', six tensor planes) over the
            CUDA-event time of those launches, against the measured HBM copy peak.  (The Gauss-Seidel sweep reads
            pre-evaluated fp16 operator rows, 20 B/voxel, instead of the 24 B of tensor planes: ncu traffic 32 B/voxel.)
-  cpu_baseline: the oracle restatement of the reference (lexicographic GS, double, 1 thread, with the
-           reference's redundant residual/norm passes) timed on a bounded sample of the same workload
+  cpu_baseline / --impl reference: the reference's own code on the host cores -- oracle/_ref/libmadref.so, the unmodified
+           reference headers compiled against the stand-in ITK (kind "reference"), or, where that library is absent, the oracle
+           port (kind "port") -- lexicographic GS, double, one independent single-threaded solve per core (the reference has no
+           threading), on a bounded sample of the same workload
 """
 from __future__ import annotations
 
@@ -134,29 +136,78 @@ def cpu_reference_run(size: int, nu: int, smoother: int, steps: int, warmup: int
     return dict(mvox_s=n * steps / dt / 1e6, s_per_cycle=dt / steps, setup_s=setup_s, relres=relres, voxels=n)
 
 
+def cpu_reference_run_ref(size: int, nu: int, smoother: int, steps: int, warmup: int):
+    """The reference's OWN code on the host: oracle/_ref/libmadref.so = the unmodified /root/reference/include headers compiled
+    against the stand-in ITK of oracle/shim.  GenerateData() is run with tolerance 0 for exactly warmup + steps V-cycles (each with
+    the stop-test residual + norm, …Filter.hxx:207-246); the set-up (GridsHierarchy + DirectSolver, timed separately through the
+    same library) is subtracted, so the figure is cycles only, like the GPU arm."""
+    import numpy as np
+
+    from multigridanisotropicdiffusion_b200 import phantom
+    from oracle import ref as R
+    shape = (size, size, size)
+    img_t, D = phantom.vessel_phantom(shape)
+    img = img_t.numpy().astype(np.float64)
+    T = phantom.planes_to_aos(D).numpy().astype(np.float64)
+    t0 = time.perf_counter()
+    h = R.Reference(shape, phantom.VED_SPACING, T, 0.1)
+    h.direct_solve(np.zeros(h.levels[-1]["shape"]))  # forces the coarsest-grid factorisation
+    setup_s = time.perf_counter() - t0
+    del h
+    ncyc = max(steps + warmup, 1)
+    t0 = time.perf_counter()
+    R.run_filter(img, phantom.VED_SPACING, T, smoother=smoother, cycle=0, nu=nu, time_step=0.1, tolerance=0.0, max_cycles=ncyc,
+                 number_of_steps=1, pixel="double", verbose=False)
+    total = time.perf_counter() - t0
+    per = max(total - setup_s, 1e-9) / ncyc
+    n = size ** 3
+    return dict(mvox_s=n / per / 1e6, s_per_cycle=per, setup_s=setup_s, relres=None, voxels=n, kind="reference")
+
+
+def cpu_impl_kind(requested="auto"):
+    """'reference' (oracle/_ref: the compiled reference headers) when that library is present, else 'port' (the C restatement)."""
+    if requested in ("reference", "port"):
+        return requested
+    from oracle import ref as R
+    return "reference" if R.available() else "port"
+
+
 def _cpu_worker(a):
-    size, nu, smoother, steps, warmup = a
-    return cpu_reference_run(size, nu, smoother, steps, warmup)
+    size, nu, smoother, steps, warmup, kind = a
+    if kind == "reference":
+        return cpu_reference_run_ref(size, nu, smoother, steps, warmup)
+    r = cpu_reference_run(size, nu, smoother, steps, warmup)
+    r["kind"] = "port"
+    return r
 
 
-def cpu_reference_all_cores(size: int, nu: int, smoother: int, steps: int, warmup: int, procs: int):
+def cpu_reference_all_cores(size: int, nu: int, smoother: int, steps: int, warmup: int, procs: int, kind: str = "port"):
     """The reference solver is single-threaded by construction (GenerateData, not ThreadedGenerateData; its Gauss-Seidel
     sweep is lexicographic), so "all the host cores" means one independent solve per core: `procs` processes each run the
     same bounded sample concurrently and the aggregate voxel rate is reported."""
     import multiprocessing as mp
     if procs <= 1:
-        r = cpu_reference_run(size, nu, smoother, steps, warmup)
+        r = _cpu_worker((size, nu, smoother, steps, warmup, kind))
         r["procs"] = 1
         return r
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        rs = pool.map(_cpu_worker, [(size, nu, smoother, steps, warmup)] * procs)
+        rs = pool.map(_cpu_worker, [(size, nu, smoother, steps, warmup, kind)] * procs)
     wall = time.perf_counter() - t0
     slowest = max(r["s_per_cycle"] for r in rs)
     n = size ** 3
     return dict(mvox_s=procs * n / slowest / 1e6, s_per_cycle=slowest, setup_s=max(r["setup_s"] for r in rs), relres=rs[0]["relres"],
-                voxels=n, procs=procs, wall_s=wall, single_core_mvox_s=rs[0]["mvox_s"])
+                voxels=n, procs=procs, wall_s=wall, single_core_mvox_s=rs[0]["mvox_s"], kind=kind)
+
+
+def cpu_sample_text(r, size, nu, cycles):
+    what = ("the reference's own code (unmodified /root/reference/include headers compiled against the stand-in ITK of oracle/shim, "
+            "oracle/_ref/libmadref.so): GenerateData() with tolerance 0, set-up subtracted" if r["kind"] == "reference" else
+            "the oracle port (C restatement, bit-identical to the reference headers) in faithful mode")
+    return (f"{r['procs']} concurrent single-threaded solves (the reference has no threading), each a {size}^3 volume of the same "
+            f"phantom/tensor, {cycles} V({nu},{nu}) cycles incl. the stop-test residual, lexicographic GS, double: {what}; "
+            f"setup {r['setup_s']:.1f}s excluded; one core alone: {r.get('single_core_mvox_s', r['mvox_s']):.3f} Mvoxel/s")
 
 
 def host_procs(limit=16):
@@ -173,18 +224,17 @@ def run_reference_arm(args):
         return
     nu, sm = args.nu, (0 if args.smoother == "gs" else 1)
     procs = host_procs()
-    r = cpu_reference_all_cores(args.cpu_size, nu, sm, args.steps, args.warmup, procs)
+    kind = cpu_impl_kind(args.cpu_impl)
+    size = args.cpu_size or (96 if kind == "reference" else 128)
+    r = cpu_reference_all_cores(size, nu, sm, args.steps, args.warmup, procs, kind)
     line = {
         "impl": "reference",
         "metric": "3D VED V-cycle Mvoxels/s at 512^3", "value": r["mvox_s"], "unit": "Mvoxel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_cycle"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, "replicas" if args.gpus > 1 else "single"),
-        "cpu_baseline": {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": "port",
-                         "sample": f"{r['procs']} concurrent single-threaded solves (the reference has no threading), each a {args.cpu_size}^3 "
-                                   f"volume of the same phantom/tensor, {args.steps} V({nu},{nu}) cycles of the oracle port in faithful mode "
-                                   "(bit-identical to the reference headers compiled against the stand-in ITK, which are slower); "
-                                   f"setup {r['setup_s']:.1f}s excluded; one core alone: {r.get('single_core_mvox_s', r['mvox_s']):.2f} Mvoxel/s"},
+        "cpu_baseline": {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": kind,
+                         "sample": cpu_sample_text(r, size, nu, args.steps + (args.warmup if kind == "reference" else 0))},
         "e2e": {"value": r["mvox_s"], "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -378,11 +428,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_all_cores(args.cpu_size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0, host_procs())
-        cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": "port",
-               "sample": f"{r['procs']} concurrent single-threaded solves (the reference has no threading), each a {args.cpu_size}^3 volume of "
-                         f"the same phantom/tensor, {args.cpu_steps} V({nu},{nu}) cycles of the oracle port in faithful mode (lexicographic GS, "
-                         f"double; setup {r['setup_s']:.1f}s excluded); one core alone: {r.get('single_core_mvox_s', r['mvox_s']):.2f} Mvoxel/s"}
+        kind = cpu_impl_kind(args.cpu_impl)
+        size = args.cpu_size or (96 if kind == "reference" else 128)
+        r = cpu_reference_all_cores(size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0, host_procs(), kind)
+        cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": kind, "sample": cpu_sample_text(r, size, nu, args.cpu_steps)}
 
     if rank == 0:
         line = {
@@ -409,7 +458,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--smoother", default="gs", choices=["gs", "wj"])
     ap.add_argument("--nu", type=int, default=3)
-    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-size", type=int, default=0, help="edge of the CPU sample volume (default: 96 for the compiled reference, 128 for the port)")
+    ap.add_argument("--cpu-impl", default="auto", choices=["auto", "reference", "port"],
+                    help="CPU legs: oracle/_ref (the compiled reference headers) when present, else the oracle port")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
