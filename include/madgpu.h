@@ -119,7 +119,7 @@ const char *madgpu_last_error(const madgpu_ctx *ctx); /* ctx may be NULL: error 
  * all-reduce per norm); levels of 64^3 voxels or fewer are gathered onto rank 0, which runs the rest of the V-cycle
  * and scatters the correction back.  Every entry point becomes a collective: all ranks call it with their own slab
  * (images, tensor) in the same order.  Requirements: 3-D, size[2] divisible by world_size, planes per rank even
- * and >= 4; FMG is not available.  NCCL is bound at run time (dlopen of libnccl.so.2).
+ * and >= 4.  NCCL is bound at run time (dlopen of libnccl.so.2).
  *   id128: 128 bytes from madgpu_nccl_unique_id() on one rank, distributed by the caller (MPI, torch.distributed, ...). */
 int madgpu_nccl_unique_id(void *id128);
 int madgpu_create_slab(const madgpu_params *p, const void *nccl_unique_id, madgpu_ctx **out);

@@ -755,6 +755,31 @@ void outer_iteration(madgpu_ctx* ctx, bool smoother_only)
   op_residual64(ctx, L.f, nullptr);                          // …Filter.hxx:215-217 / :237-239
 }
 
+void fmg(madgpu_ctx* ctx);
+
+// FullMultiGrid below the agglomeration level of a slab context: the restricted right-hand side of that level is gathered onto
+// rank 0, whose serial sub-hierarchy runs its own FullMultiGrid on it (its level 0 IS the agglomeration level, so the nu V-cycles
+// of that level, …Filter.hxx:332, are part of it), and the iterate is scattered back.  Not yet run on a multi-GPU box.
+void agglomerated_fmg(madgpu_ctx* ctx)
+{
+  Level& L = ctx->lv[ctx->nlevels - 1];
+  Scope s(ctx, MADGPU_K_COARSE, 0);
+  pack_slab(ctx, L, L.f, ctx->slab_buf);
+  gather_slabs(ctx, L);
+  if (ctx->rank == 0) {
+    madgpu_ctx* S = ctx->sub;
+    Level& S0 = S->lv[0];
+    const dim3 b = block3(3), g = grid3(S0.g, b);
+    k_dense_to_pitched<float, double><<<g, b, 0, S->stream>>>(S0.g, ctx->gather_buf, S->f64);
+    fmg(S);  // -> S->u64
+    k_pitched_to_dense<double, float><<<g, b, 0, S->stream>>>(S0.g, S->u64, ctx->gather_buf);
+    ctx->launches += S->launches + 2;
+    S->launches = 0;
+  }
+  scatter_slabs(ctx, L);
+  unpack_slab(ctx, L, ctx->slab_buf, L.u);
+}
+
 // Full multigrid prologue: itkMultigridAnisotropicDiffusionImageFilter.hxx:300-338.  Produces u64.
 void fmg(madgpu_ctx* ctx)
 {
@@ -773,8 +798,9 @@ void fmg(madgpu_ctx* ctx)
   // rhs restricted all the way down (:324-326)
   op_restrict<double>(ctx, 0, ctx->f64, ctx->lv[1].f);
   for (int l = 1; l < Lmax; ++l) op_restrict<float>(ctx, l, ctx->lv[l].f, ctx->lv[l + 1].f);
-  // coarsest: zero guess, nu V-cycles == direct solve (:311-314)
-  vcycle(ctx, Lmax);
+  // coarsest: zero guess, nu V-cycles == direct solve (:311-314); on z-slabs the rest of the recursion runs on rank 0
+  if (ctx->world > 1) agglomerated_fmg(ctx);
+  else vcycle(ctx, Lmax);
   for (int l = Lmax - 1; l >= 1; --l) {
     op_prolong<float, false>(ctx, l, ctx->lv[l + 1].u, ctx->lv[l].u);  // :330
     for (int it = 0; it < nu; ++it) vcycle(ctx, l);                     // :332
@@ -1186,7 +1212,6 @@ int check_ready(madgpu_ctx* ctx)
   if (!ctx) return MADGPU_EINVAL;
   if (!ctx->tensor_set) return fail(ctx, MADGPU_ESTATE, "diffusion tensor not set (call madgpu_set_tensor_* first)");
   if (ctx->p.number_of_steps < 1) return fail(ctx, MADGPU_EINVAL, "number_of_steps must be >= 1");
-  if (ctx->world > 1 && ctx->p.cycle == MADGPU_CYCLE_FMG) return fail(ctx, MADGPU_ESTATE, "FMG is not available on a z-slab context (world_size > 1)");
   if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
   return 0;
 }

@@ -1,0 +1,63 @@
+"""Run under torchrun with >= 2 GPUs (tests/test_zz_gpu_multi_fmg.py does): FullMultiGrid on z-slabs.
+
+The FMG prologue below the agglomeration level runs on rank 0's serial sub-hierarchy (agglomerated_fmg, csrc/madgpu.cu); above
+it the prolongations and the nu V-cycles per level are distributed.  Weighted Jacobi is then the same iteration as on one GPU
+(cycle counts, per-cycle residuals, image); Gauss-Seidel is compared on the converged image."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from multigridanisotropicdiffusion_b200 import MadSolver, phantom, slabs  # noqa: E402
+from util import rel_l2  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ok = True
+    shape = (128, 96, 160)
+    img_t, D = phantom.vessel_phantom(shape)
+    img = img_t.numpy()
+    T = phantom.planes_to_aos(D).numpy()
+    for smoother, name in ((MadSolver.WJ, "wj"), (MadSolver.GS, "gs")):
+        kw = dict(time_step=0.1, smoother=smoother, iterations_per_grid=2, cycle=MadSolver.FMG, tolerance=1e-9, max_cycles=40, number_of_steps=2)
+        s = MadSolver(shape, phantom.VED_SPACING, device=local_rank, rank=rank, world_size=world, nccl_id=slabs.create_unique_id(), **kw)
+        s.set_tensor(slabs.cut(T, rank, world))
+        out_local = s.solve(slabs.cut(img, rank, world), out_dtype=np.float64)
+        st = s.last_stats
+        full = slabs.gather_volume(out_local)
+        s.close()
+        if rank == 0:
+            r = MadSolver(shape, phantom.VED_SPACING, device=local_rank, **kw)
+            r.set_tensor(T)
+            ref = r.solve(img, out_dtype=np.float64)
+            rst = r.last_stats
+            r.close()
+            err = rel_l2(full, ref)
+            print(f"[fmg {name} world {world}] cycles slab {st['cycles_per_step'][:2]} single {rst['cycles_per_step'][:2]} rel-L2 {err:.3e} "
+                  f"relres {st['final_relres'][:2]}", flush=True)
+            good = err < (1e-6 if name == "wj" else 1e-5) and all(x <= 1e-9 for x in st["final_relres"][:2])
+            if name == "wj":
+                good = good and st["cycles_per_step"][:2] == rst["cycles_per_step"][:2]
+            else:
+                good = good and all(abs(a - b) <= 2 for a, b in zip(st["cycles_per_step"][:2], rst["cycles_per_step"][:2]))
+            ok = ok and good
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    if rank == 0 and flag.item():
+        print("MULTI_GPU_FMG_OK", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
