@@ -17,6 +17,14 @@
 #include "mad_kernels.cuh"
 #include "mad_fast.cuh"
 
+// Every kernel launch of this file goes through MAD_LAUNCH((kernel<...>), grid, block, shared bytes, stream, args...) -- the kernel
+// name in parentheses so that template commas survive the preprocessor.  Here it is the plain <<<>>> launch; the CPU test build
+// (tests/mad_host/) defines it beforehand to run the same kernel source on host fibres.
+#ifndef MAD_LAUNCH
+#define MAD_UNPAREN(...) __VA_ARGS__
+#define MAD_LAUNCH(kernel, grid, block, smem, stream, ...) MAD_UNPAREN kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -199,7 +207,7 @@ size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT
   do {                                                                                                                       \
     const int zc = fast_zc(L.g, WY);                                                                                         \
     const dim3 fg = fast_grid(L.g, WY, zc);                                                                                  \
-    fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF><<<fg, dim3(32, WY), 0, ctx->stream>>>(gg, D, u, f, out, partials, omega, zc, ctx->pf_dist, uzero); \
+    MAD_LAUNCH((fast::k_fast_sweep<MODE, T, UT, FT, OT, WY, MINB, PF>), fg, dim3(32, WY), 0, ctx->stream, gg, D, u, f, out, partials, omega, zc, ctx->pf_dist, uzero); \
     if (MODE != fast::MODE_COEF) halo_signal(ctx, out);                                                                      \
     return (size_t)fg.x * fg.y * fg.z;                                                                                       \
   } while (0)
@@ -408,13 +416,13 @@ void exchange_halo(madgpu_ctx* ctx, const Level& L, T* field)
 void pack_slab(madgpu_ctx* ctx, const Level& L, const float* pitched, float* dense)
 {
   const dim3 b = block3(3), g = grid3(L.g, b);
-  k_pitched_to_dense<float, float><<<g, b, 0, ctx->stream>>>(L.g, pitched, dense);
+  MAD_LAUNCH((k_pitched_to_dense<float, float>), g, b, 0, ctx->stream, L.g, pitched, dense);
   ctx->launches++;
 }
 void unpack_slab(madgpu_ctx* ctx, const Level& L, const float* dense, float* pitched)
 {
   const dim3 b = block3(3), g = grid3(L.g, b);
-  k_dense_to_pitched<float, float><<<g, b, 0, ctx->stream>>>(L.g, dense, pitched);
+  MAD_LAUNCH((k_dense_to_pitched<float, float>), g, b, 0, ctx->stream, L.g, dense, pitched);
   halo_dirty(ctx, pitched);
   ctx->launches++;
 }
@@ -496,8 +504,8 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
     if (smoother == MADGPU_SMOOTHER_WJ) {
       Scope s(ctx, cls);
       if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega, uz);
-      else if (ctx->dim == 3) k_jacobi<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
-      else k_jacobi<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
+      else if (ctx->dim == 3) MAD_LAUNCH((k_jacobi<3>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
+      else MAD_LAUNCH((k_jacobi<2>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       if (!use_fast(ctx, L)) halo_dirty(ctx, L.tmp);
       std::swap(L.u, L.tmp);
     } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16) {
@@ -517,10 +525,10 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       Scope s(ctx, cls);
       if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
         const int zc = fast_zc(L.g, 8);
-        fast::k_coef_gs2<4, 3><<<fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream>>>(gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_coef_gs2<4, 3>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_coef_gs<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_coef_gs<4, 4>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
       std::swap(L.u, L.tmp);
       halo_signal(ctx, L.u);
@@ -529,25 +537,25 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       Scope s(ctx, cls);
       if (ctx->fast_cfg == 1) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<8, 1, false, false>), fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 4) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 2, true, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<4, 2, true, false>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 5) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, true, false><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<8, 1, true, false>), fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 7) {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false, true><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<4, 3, false, true>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 8) {
         const int zc = fast_zc(L.g, 8);
-        fast::k_fast_gs<8, 1, false, true><<<fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<8, 1, false, true>), fast_grid(L.g, 8, zc), dim3(32, 8), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else if (ctx->fast_cfg == 6) {
         const int zc = fast_zc(L.g, 2);
-        fast::k_fast_gs<2, 6, false, false><<<fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<2, 6, false, false>), fast_grid(L.g, 2, zc), dim3(32, 2), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
         const int zc = fast_zc(L.g, 4);
-        fast::k_fast_gs<4, 3, false, false><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        MAD_LAUNCH((fast::k_fast_gs<4, 3, false, false>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, D, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       }
       std::swap(L.u, L.tmp);
       halo_signal(ctx, L.u);
@@ -555,8 +563,8 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       const int nc = ctx->dim == 2 ? 4 : (ctx->p.gs_colors == 8 ? 8 : 4);
       Scope s(ctx, cls, nc);
       for (int c = 0; c < nc; ++c) {
-        if (ctx->dim == 3) k_gs_color<3><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, c, nc);
-        else k_gs_color<2><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, c, nc);
+        if (ctx->dim == 3) MAD_LAUNCH((k_gs_color<3>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, c, nc);
+        else MAD_LAUNCH((k_gs_color<2>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, c, nc);
       }
       halo_dirty(ctx, L.u);
     }
@@ -573,7 +581,7 @@ double read_scalar(madgpu_ctx* ctx)
 // sum of the per-block partials -> d_scalar (device); caller reads it back when needed
 void reduce_partials(madgpu_ctx* ctx, size_t n)
 {
-  k_reduce_partials<<<1, 1024, 0, ctx->stream>>>(ctx->partials, (long long)n, ctx->d_scalar);
+  MAD_LAUNCH((k_reduce_partials), 1, 1024, 0, ctx->stream, ctx->partials, (long long)n, ctx->d_scalar);
   if (ctx->world > 1) NCV(g_nccl.AllReduce(ctx->d_scalar, ctx->d_scalar, 1, Nccl::Float64, Nccl::Sum, ctx->comm, ctx->stream));
 }
 
@@ -591,7 +599,7 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
     const int zc = fast_zc(L.g, 4);
     Geom gg = L.g;
     set_ghosts(ctx, gg, L, out, sizeof(float));
-    fast::k_coef_residual<4, 4><<<fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream>>>(gg, L.coef16, L.u, L.f, out, zc, ctx->pf_dist);
+    MAD_LAUNCH((fast::k_coef_residual<4, 4>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, out, zc, ctx->pf_dist);
     halo_signal(ctx, out);
     return;
   }
@@ -600,8 +608,8 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
     if (norm) reduce_partials(ctx, nb);
     return;
   }
-  if (ctx->dim == 3) k_residual<3, float, float, float, float><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, out, part);
-  else k_residual<2, float, float, float, float><<<g, b, 0, ctx->stream>>>(L.g, D, L.u, L.f, out, part);
+  if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, float, float, float, float>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, out, part);
+  else MAD_LAUNCH((k_residual<2, float, float, float, float>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, out, part);
   halo_dirty(ctx, out);
   if (norm) reduce_partials(ctx, (size_t)g.x * g.y * g.z);
 }
@@ -615,15 +623,15 @@ void op_residual64(madgpu_ctx* ctx, float* r32_or_null, double* r64_or_null)
   Scope s(ctx, MADGPU_K_RESID0, 2);
   const Tensor D = tensor_of(L);
   if (r64_or_null) {
-    if (ctx->dim == 3) k_residual<3, double, double, double, double><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
-    else k_residual<2, double, double, double, double><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
+    if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, double, double, double, double>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
+    else MAD_LAUNCH((k_residual<2, double, double, double, double>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
   } else if (use_fast(ctx, L)) {
     const size_t nb = launch_fast<fast::MODE_RES, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f);
     reduce_partials(ctx, nb);
     return;
   } else {
-    if (ctx->dim == 3) k_residual<3, double, double, double, float><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
-    else k_residual<2, double, double, double, float><<<g, b, 0, ctx->stream>>>(L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
+    if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, double, double, double, float>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
+    else MAD_LAUNCH((k_residual<2, double, double, double, float>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
   }
   reduce_partials(ctx, (size_t)g.x * g.y * g.z);
 }
@@ -648,12 +656,12 @@ void op_restrict(madgpu_ctx* ctx, int lf, const TI* fine, float* coarse, int cls
     if (use_fast(ctx, F) && F.g.nx >= 8) {
       constexpr int WY = 8;
       const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (C.g.ny + WY - 1) / WY, C.g.nz);
-      fast::k_fast_restrict<WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(F.g, C.g, transfer_of(C), fine, coarse);
+      MAD_LAUNCH((fast::k_fast_restrict<WY>), fg, dim3(32, WY), 0, ctx->stream, F.g, C.g, transfer_of(C), fine, coarse);
       return;
     }
   }
-  if (ctx->dim == 3) k_restrict<3, TI, float><<<g, b, 0, ctx->stream>>>(F.g, C.g, transfer_of(C), fine, coarse);
-  else k_restrict<2, TI, float><<<g, b, 0, ctx->stream>>>(F.g, C.g, transfer_of(C), fine, coarse);
+  if (ctx->dim == 3) MAD_LAUNCH((k_restrict<3, TI, float>), g, b, 0, ctx->stream, F.g, C.g, transfer_of(C), fine, coarse);
+  else MAD_LAUNCH((k_restrict<2, TI, float>), g, b, 0, ctx->stream, F.g, C.g, transfer_of(C), fine, coarse);
 }
 
 template <typename TO, bool ADD>
@@ -671,13 +679,13 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
       const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, (F.g.nz + fast::PROLONG_ZB - 1) / fast::PROLONG_ZB);
       Geom gg = F.g;
       set_ghosts(ctx, gg, F, fine, sizeof(float));
-      fast::k_fast_prolong<ADD, WY><<<fg, dim3(32, WY), 0, ctx->stream>>>(C.g, gg, transfer_of(C), coarse, fine);
+      MAD_LAUNCH((fast::k_fast_prolong<ADD, WY>), fg, dim3(32, WY), 0, ctx->stream, C.g, gg, transfer_of(C), coarse, fine);
       halo_signal(ctx, fine);
       return;
     }
   }
-  if (ctx->dim == 3) k_prolong<3, TO, ADD><<<g, b, 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
-  else k_prolong<2, TO, ADD><<<g, b, 0, ctx->stream>>>(C.g, F.g, transfer_of(C), coarse, fine);
+  if (ctx->dim == 3) MAD_LAUNCH((k_prolong<3, TO, ADD>), g, b, 0, ctx->stream, C.g, F.g, transfer_of(C), coarse, fine);
+  else MAD_LAUNCH((k_prolong<2, TO, ADD>), g, b, 0, ctx->stream, C.g, F.g, transfer_of(C), coarse, fine);
   halo_dirty(ctx, fine);
 }
 
@@ -688,7 +696,7 @@ void op_coarse_solve(madgpu_ctx* ctx)
     Scope s(ctx, MADGPU_K_COARSE);
     const int n = ctx->ncoarse;
     const int rows_per_block = 8;
-    k_coarse_gemv<<<(n + rows_per_block - 1) / rows_per_block, 32 * rows_per_block, n * sizeof(double), ctx->stream>>>(L.g, ctx->Ainv, L.f, L.u, n);
+    MAD_LAUNCH((k_coarse_gemv), (n + rows_per_block - 1) / rows_per_block, 32 * rows_per_block, n * sizeof(double), ctx->stream, L.g, ctx->Ainv, L.f, L.u, n);
   } else {
     // Coarsest grid too large for a dense inverse (thin volumes stop coarsening early): iterate the
     // multicolour Gauss-Seidel smoother to fp32 convergence instead of vnl_sparse_lu.
@@ -696,7 +704,7 @@ void op_coarse_solve(madgpu_ctx* ctx)
     const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
     {
       Scope s(ctx, MADGPU_K_COARSE, 2);
-      k_sumsq<float><<<g, b, 0, ctx->stream>>>(L.g, L.f, ctx->partials);
+      MAD_LAUNCH((k_sumsq<float>), g, b, 0, ctx->stream, L.g, L.f, ctx->partials);
       reduce_partials(ctx, (size_t)g.x * g.y * g.z);
     }
     const double f_norm = std::sqrt(read_scalar(ctx));
@@ -740,7 +748,7 @@ void op_axpy(madgpu_ctx* ctx)
   Scope s(ctx, MADGPU_K_MISC);
   Geom gg = L.g;
   set_ghosts(ctx, gg, L, ctx->u64, sizeof(double));
-  k_axpy_f64_f32<<<g, b, 0, ctx->stream>>>(gg, ctx->u64, L.u);
+  MAD_LAUNCH((k_axpy_f64_f32), g, b, 0, ctx->stream, gg, ctx->u64, L.u);
   halo_signal(ctx, ctx->u64);
 }
 
@@ -770,9 +778,9 @@ void agglomerated_fmg(madgpu_ctx* ctx)
     madgpu_ctx* S = ctx->sub;
     Level& S0 = S->lv[0];
     const dim3 b = block3(3), g = grid3(S0.g, b);
-    k_dense_to_pitched<float, double><<<g, b, 0, S->stream>>>(S0.g, ctx->gather_buf, S->f64);
+    MAD_LAUNCH((k_dense_to_pitched<float, double>), g, b, 0, S->stream, S0.g, ctx->gather_buf, S->f64);
     fmg(S);  // -> S->u64
-    k_pitched_to_dense<double, float><<<g, b, 0, S->stream>>>(S0.g, S->u64, ctx->gather_buf);
+    MAD_LAUNCH((k_pitched_to_dense<double, float>), g, b, 0, S->stream, S0.g, S->u64, ctx->gather_buf);
     ctx->launches += S->launches + 2;
     S->launches = 0;
   }
@@ -1091,8 +1099,8 @@ int set_tensor_host(madgpu_ctx* ctx, const T* aos)
     CU(cudaMemcpyAsync(stage[k], aos + first * nc, (size_t)cnt * nc * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     const int th = 256;
     const unsigned bl = (unsigned)((cnt + th - 1) / th);
-    if (nc == 6) k_tensor_ingest<T, 6><<<bl, th, 0, ctx->stream>>>(L.g, stage[k], first, cnt, nullptr, L.D[0], L.D[1], L.D[2], L.D[3], L.D[4], L.D[5]);
-    else k_tensor_ingest<T, 3><<<bl, th, 0, ctx->stream>>>(L.g, stage[k], first, cnt, nullptr, L.D[0], L.D[1], L.D[2], nullptr, nullptr, nullptr);
+    if (nc == 6) MAD_LAUNCH((k_tensor_ingest<T, 6>), bl, th, 0, ctx->stream, L.g, stage[k], first, cnt, nullptr, L.D[0], L.D[1], L.D[2], L.D[3], L.D[4], L.D[5]);
+    else MAD_LAUNCH((k_tensor_ingest<T, 3>), bl, th, 0, ctx->stream, L.g, stage[k], first, cnt, nullptr, L.D[0], L.D[1], L.D[2], nullptr, nullptr, nullptr);
     CU(cudaEventRecord(done[k], ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1109,10 +1117,10 @@ int stage_input(madgpu_ctx* ctx, int type, const void* dev_dense)
   Level& L = ctx->lv[0];
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   switch (type) {
-    case MADGPU_PIX_U8: k_dense_to_pitched<uint8_t, double><<<g, b, 0, ctx->stream>>>(L.g, (const uint8_t*)dev_dense, ctx->f64); break;
-    case MADGPU_PIX_I16: k_dense_to_pitched<int16_t, double><<<g, b, 0, ctx->stream>>>(L.g, (const int16_t*)dev_dense, ctx->f64); break;
-    case MADGPU_PIX_F32: k_dense_to_pitched<float, double><<<g, b, 0, ctx->stream>>>(L.g, (const float*)dev_dense, ctx->f64); break;
-    case MADGPU_PIX_F64: k_dense_to_pitched<double, double><<<g, b, 0, ctx->stream>>>(L.g, (const double*)dev_dense, ctx->f64); break;
+    case MADGPU_PIX_U8: MAD_LAUNCH((k_dense_to_pitched<uint8_t, double>), g, b, 0, ctx->stream, L.g, (const uint8_t*)dev_dense, ctx->f64); break;
+    case MADGPU_PIX_I16: MAD_LAUNCH((k_dense_to_pitched<int16_t, double>), g, b, 0, ctx->stream, L.g, (const int16_t*)dev_dense, ctx->f64); break;
+    case MADGPU_PIX_F32: MAD_LAUNCH((k_dense_to_pitched<float, double>), g, b, 0, ctx->stream, L.g, (const float*)dev_dense, ctx->f64); break;
+    case MADGPU_PIX_F64: MAD_LAUNCH((k_dense_to_pitched<double, double>), g, b, 0, ctx->stream, L.g, (const double*)dev_dense, ctx->f64); break;
     default: return fail(ctx, MADGPU_EINVAL, "bad pixel type %d", type);
   }
   ctx->launches++;
@@ -1124,10 +1132,10 @@ int stage_output(madgpu_ctx* ctx, int type, void* dev_dense)
   Level& L = ctx->lv[0];
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   switch (type) {
-    case MADGPU_PIX_U8: k_pitched_to_dense<double, uint8_t><<<g, b, 0, ctx->stream>>>(L.g, ctx->u64, (uint8_t*)dev_dense); break;
-    case MADGPU_PIX_I16: k_pitched_to_dense<double, int16_t><<<g, b, 0, ctx->stream>>>(L.g, ctx->u64, (int16_t*)dev_dense); break;
-    case MADGPU_PIX_F32: k_pitched_to_dense<double, float><<<g, b, 0, ctx->stream>>>(L.g, ctx->u64, (float*)dev_dense); break;
-    case MADGPU_PIX_F64: k_pitched_to_dense<double, double><<<g, b, 0, ctx->stream>>>(L.g, ctx->u64, (double*)dev_dense); break;
+    case MADGPU_PIX_U8: MAD_LAUNCH((k_pitched_to_dense<double, uint8_t>), g, b, 0, ctx->stream, L.g, ctx->u64, (uint8_t*)dev_dense); break;
+    case MADGPU_PIX_I16: MAD_LAUNCH((k_pitched_to_dense<double, int16_t>), g, b, 0, ctx->stream, L.g, ctx->u64, (int16_t*)dev_dense); break;
+    case MADGPU_PIX_F32: MAD_LAUNCH((k_pitched_to_dense<double, float>), g, b, 0, ctx->stream, L.g, ctx->u64, (float*)dev_dense); break;
+    case MADGPU_PIX_F64: MAD_LAUNCH((k_pitched_to_dense<double, double>), g, b, 0, ctx->stream, L.g, ctx->u64, (double*)dev_dense); break;
     default: return fail(ctx, MADGPU_EINVAL, "bad pixel type %d", type);
   }
   ctx->launches++;
@@ -1153,7 +1161,7 @@ int run_steps(madgpu_ctx* ctx)
     // rhsNorm (:204)
     {
       Scope s(ctx, MADGPU_K_MISC, 2);
-      k_sumsq<double><<<g, b, 0, ctx->stream>>>(L.g, ctx->f64, ctx->partials);
+      MAD_LAUNCH((k_sumsq<double>), g, b, 0, ctx->stream, L.g, ctx->f64, ctx->partials);
       reduce_partials(ctx, (size_t)g.x * g.y * g.z);
     }
     const double rhs_norm = std::sqrt(read_scalar(ctx));
@@ -1493,7 +1501,7 @@ int madgpu_set_tensor_device_f32(madgpu_ctx* ctx, const float* const* planes)
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   for (int c = 0; c < ctx->ncomp; ++c) {
     if (!planes[c]) return fail(ctx, MADGPU_EINVAL, "null tensor plane %d", c);
-    k_dense_to_pitched<float, float><<<g, b, 0, ctx->stream>>>(L.g, planes[c], L.D[c]);
+    MAD_LAUNCH((k_dense_to_pitched<float, float>), g, b, 0, ctx->stream, L.g, planes[c], L.D[c]);
   }
   const int rc = finish_tensor(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1566,7 +1574,7 @@ static int cycles_begin_common(madgpu_ctx* ctx)
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   halo_dirty(ctx, ctx->u64);
   CU(cudaMemcpyAsync(ctx->u64, ctx->f64, bytes64, cudaMemcpyDeviceToDevice, ctx->stream));
-  k_sumsq<double><<<g, b, 0, ctx->stream>>>(L.g, ctx->f64, ctx->partials);
+  MAD_LAUNCH((k_sumsq<double>), g, b, 0, ctx->stream, L.g, ctx->f64, ctx->partials);
   reduce_partials(ctx, (size_t)g.x * g.y * g.z);
   ctx->rhs_norm = std::sqrt(read_scalar(ctx));
   op_residual64(ctx, L.f, nullptr);
@@ -1847,8 +1855,8 @@ int madgpu_op_assemble(madgpu_ctx* ctx, int32_t level, float* stencil)
   float* d = nullptr;
   CU(cudaMalloc((void**)&d, nv * ns * sizeof(float)));
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
-  if (ctx->dim == 3) k_assemble<3><<<g, b, 0, ctx->stream>>>(L.g, tensor_of(L), d);
-  else k_assemble<2><<<g, b, 0, ctx->stream>>>(L.g, tensor_of(L), d);
+  if (ctx->dim == 3) MAD_LAUNCH((k_assemble<3>), g, b, 0, ctx->stream, L.g, tensor_of(L), d);
+  else MAD_LAUNCH((k_assemble<2>), g, b, 0, ctx->stream, L.g, tensor_of(L), d);
   cudaError_t e = cudaMemcpyAsync(stencil, d, nv * ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d);
