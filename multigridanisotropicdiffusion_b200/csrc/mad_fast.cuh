@@ -29,6 +29,13 @@ namespace fast {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TX = 128;  // voxels per warp row
 
+// L2 prefetch without a register destination (PTX); a no-op in the CPU test build (tests/mad_host/)
+#ifndef MAD_HOST_EMULATION
+__device__ __forceinline__ void mad_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+inline void mad_prefetch_l2(const void*) {}
+#endif
+
 template <typename T>
 struct V4 {
   T v[4];
@@ -242,8 +249,8 @@ __device__ __forceinline__ Prefetch make_prefetch(const Geom& g, const Tensor& D
 __device__ __forceinline__ void prefetch_plane(const Prefetch& P, int z)
 {
   const char* q = P.a + P.stride * z;
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-  if (P.b) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.b + P.stride * z));
+  mad_prefetch_l2((q));
+  if (P.b) mad_prefetch_l2((P.b + P.stride * z));
 }
 
 // first / last plane of a slab: the same row also goes to the neighbour's ghost plane (peer store over NVLink)
@@ -575,8 +582,10 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 // New values travel: own row -> registers; x-neighbours -> warp shuffles; rows y+-1 of the plane
 // being updated and of the plane below -> shared memory (two row buffers, alternating with z).
 // ------------------------------------------------------------------------------------------
+#ifndef MAD_HOST_EMULATION
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#endif  // the CPU test build (tests/mad_host/) supplies named barriers of its own
 
 template <int WY, int MINB, bool PF, bool SPLIT>
 __global__ void __launch_bounds__(32 * WY, MINB) k_fast_gs(Geom g, Tensor D, const float* __restrict__ u, const float* __restrict__ f,
@@ -781,7 +790,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
   for (int z = z0; z < z1; ++z) {
     const int oc = z * (int)g.plane + rowo;
     const int cb = z & 1, pb = cb ^ 1;
-    if (pfd > 0 && z + pfd < zpf_end && pf && !(uzero && p.lane < 4)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + pf_stride * (z + pfd)));
+    if (pfd > 0 && z + pfd < zpf_end && pf && !(uzero && p.lane < 4)) mad_prefetch_l2((pf + pf_stride * (z + pfd)));
     const CoefRaw c = issue_coef(coef, g, p, y, z);
     const Raw4<float> rf = issue4(f, oc);
     if (uzero) zero_uplane(up);
@@ -983,7 +992,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_residual(Geom g, const u
   }
   for (int z = z0; z < z1; ++z) {
     const int oc = z * (int)g.plane + rowo;
-    if (pfd > 0 && z + pfd < zpf_end && pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + pf_stride * (z + pfd)));
+    if (pfd > 0 && z + pfd < zpf_end && pf) mad_prefetch_l2((pf + pf_stride * (z + pfd)));
     const URaw<float> ru = issue_u(u, zmirror_hi(g, z) * (int)g.plane + rowo, p);
     const CoefRaw c = issue_coef(coef, g, p, p.y, z);
     const Raw4<float> rf = issue4(f, oc);

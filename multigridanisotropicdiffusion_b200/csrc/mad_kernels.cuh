@@ -21,6 +21,11 @@
 #include <stdint.h>
 #include <type_traits>
 
+// dynamic shared memory of a kernel; the CPU test build (tests/mad_host/) hands out its own block
+#ifndef MAD_DYNAMIC_SHARED
+#define MAD_DYNAMIC_SHARED(type, name) extern __shared__ type name[]
+#endif
+
 namespace mad {
 
 struct Geom {
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(256) k_prolong(Geom gc, Geom gf, Transfer t, c
 __global__ void __launch_bounds__(256) k_coarse_gemv(Geom g, const double* __restrict__ Ainv, const float* __restrict__ f, float* __restrict__ e,
                                                      int n)
 {
-  extern __shared__ double sf[];
+  MAD_DYNAMIC_SHARED(double, sf);
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     const int x = j % g.nx, y = (j / g.nx) % g.ny, z = j / (g.nx * g.ny);
     sf[j] = (double)f[(long long)z * g.plane + (long long)y * g.pitch + x];
