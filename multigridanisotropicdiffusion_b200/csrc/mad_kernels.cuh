@@ -166,7 +166,7 @@ __host__ __device__ __forceinline__ void scatter_row(const Geom& g, const Row<T>
 #undef MAD_AT
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(MAD_HOST_EMULATION)  // the CPU test build (tests/mad_host/) runs these kernels on host fibres
 
 __device__ __forceinline__ double warp_sum(double v)
 {

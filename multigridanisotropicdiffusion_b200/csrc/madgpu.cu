@@ -287,10 +287,10 @@ Nccl g_nccl = {};
 const char* nccl_load()
 {
   if (g_nccl.lib) return nullptr;
-  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  const char* names[] = {getenv("MADGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};  // MADGPU_NCCL_LIB: a specific build, e.g. the one bundled with torch
   void* h = nullptr;
   for (const char* n : names)
-    if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
   if (!h) return "libnccl.so.2 not found (needed only for world_size > 1)";
 #define MAD_SYM(field, name)                                             \
   *(void**)(&g_nccl.field) = dlsym(h, name);                             \
@@ -860,11 +860,13 @@ int plan_slabs(int nlev, const int sizes[][3], int world, std::string& why)
   if (sizes[0][2] % world != 0) { why = "size[2] must be divisible by world_size"; return -1; }
   int lnz = sizes[0][2] / world;
   int La = 0;
+  long long small = 64ll * 64 * 64;  // levels of this many voxels or fewer are latency-bound: agglomerate (MADGPU_AGGLOMERATE_VOXELS)
+  if (const char* e = getenv("MADGPU_AGGLOMERATE_VOXELS")) small = atoll(e);
   for (int l = 0; l + 1 < nlev; ++l) {
     // can level l be distributed, i.e. can its slabs be restricted to slabs of level l+1?
     const bool ok = sizes[l][2] % 2 == 0 && lnz % 2 == 0 && lnz >= 4;
     const long long vox = (long long)sizes[l][0] * sizes[l][1] * sizes[l][2];
-    if (!ok || (l > 0 && vox <= 64ll * 64 * 64)) break;  // small levels are latency-bound: agglomerate
+    if (!ok || (l > 0 && vox <= small)) break;
     lnz /= 2;
     La = l + 1;
   }

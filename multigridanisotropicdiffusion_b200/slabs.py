@@ -32,13 +32,15 @@ def plan(size_xyz, world_size):
         raise ValueError("the volume has a single level, nothing to distribute")
     if sizes[0][2] % world_size:
         raise ValueError("size[2] must be divisible by world_size")
+    import os
     lnz = sizes[0][2] // world_size
     planes = [lnz]
     la = 0
+    small = int(os.environ.get("MADGPU_AGGLOMERATE_VOXELS", 64 ** 3))  # the library's tuning hook
     for l in range(len(sizes) - 1):
         ok = sizes[l][2] % 2 == 0 and lnz % 2 == 0 and lnz >= 4
         vox = sizes[l][0] * sizes[l][1] * sizes[l][2]
-        if not ok or (l > 0 and vox <= 64 ** 3):
+        if not ok or (l > 0 and vox <= small):
             break
         lnz //= 2
         planes.append(lnz)

@@ -6,18 +6,41 @@
 #ifndef FAKE_CUDA_RUNTIME_H
 #define FAKE_CUDA_RUNTIME_H
 
+#include <sched.h>
+
 #include <chrono>
+#include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
+// ---- vector types and dim3 (what the kernels of csrc/ use of vector_types.h) ----
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+struct uint3 { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+
 enum cudaError_t { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaEventDisableTiming = 2, cudaEnableDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 struct FakeStream { int unused; };
 typedef FakeStream* cudaStream_t;  // in-order and synchronous
 struct FakeEvent { std::chrono::steady_clock::time_point t; };
 typedef FakeEvent* cudaEvent_t;
 enum { cudaStreamNonBlocking = 1 };
-struct cudaDeviceProp { int major, minor; };
+struct cudaDeviceProp { int major, minor; char name[64]; };
 
 namespace fake_cuda { inline int g_devices = 1; inline long long g_live_allocs = 0; }
 
@@ -31,10 +54,10 @@ inline cudaError_t cudaMalloc(void** p, size_t bytes)
   *p = std::malloc(bytes ? bytes : 1);
   if (!*p) return cudaErrorMemoryAllocation;
   std::memset(*p, 0xFF, bytes);  // NaN pattern for floats and doubles
-  ++fake_cuda::g_live_allocs;
+  __atomic_add_fetch(&fake_cuda::g_live_allocs, 1, __ATOMIC_RELAXED);
   return cudaSuccess;
 }
-inline cudaError_t cudaFree(void* p) { if (p) { std::free(p); --fake_cuda::g_live_allocs; } return cudaSuccess; }
+inline cudaError_t cudaFree(void* p) { if (p) { std::free(p); __atomic_sub_fetch(&fake_cuda::g_live_allocs, 1, __ATOMIC_RELAXED); } return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, bytes); return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new FakeStream(); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
@@ -47,6 +70,60 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 {
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
+}
+
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { std::memmove(dst, src, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { std::memset(p, v, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
+{
+  for (size_t r = 0; r < height; ++r) std::memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  return cudaSuccess;
+}
+inline cudaError_t cudaMallocHost(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+// "device memory" is this process's heap and every rank of a multi-rank test is a thread of it: an IPC handle is the pointer
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// stream memory operations (the driver entry points the peer-memory halo binds): the stream is synchronous, so a write is a
+// release store and a wait blocks the calling rank (thread) until the value arrives.  A wait that lasts FAKE_CUDA_WAIT_TIMEOUT_S
+// seconds (default 60) reports what it was waiting for and aborts -- on a GPU that would be a hung stream.
+namespace fake_cuda
+{
+inline int stream_write_value32(cudaStream_t, unsigned long long addr, uint32_t value, unsigned)
+{
+  __atomic_store_n(reinterpret_cast<uint32_t*>(addr), value, __ATOMIC_RELEASE);
+  return 0;
+}
+inline int stream_wait_value32(cudaStream_t, unsigned long long addr, uint32_t value, unsigned flags)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  const char* e = std::getenv("FAKE_CUDA_WAIT_TIMEOUT_S");
+  const double limit = e ? std::atof(e) : 60.0;
+  for (unsigned long spin = 0;; ++spin) {
+    const uint32_t cur = __atomic_load_n(reinterpret_cast<uint32_t*>(addr), __ATOMIC_ACQUIRE);
+    if (flags == 1 ? (int32_t)(cur - value) >= 0 : cur == value) return 0;  // 1 = CU_STREAM_WAIT_VALUE_GEQ, 0 = EQ
+    if ((spin & 1023) == 1023) {
+      sched_yield();
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit) {
+        std::fprintf(stderr, "fake_cuda: stream wait on %p for value %u timed out (current %u) -- a hung stream on a GPU\n", (void*)addr, value, cur);
+        std::abort();
+      }
+    }
+  }
+}
+}  // namespace fake_cuda
+inline cudaError_t cudaGetDriverEntryPoint(const char* name, void** f, unsigned long long, cudaDriverEntryPointQueryResult* q = nullptr)
+{
+  *f = nullptr;
+  if (!std::strcmp(name, "cuStreamWriteValue32")) *f = (void*)&fake_cuda::stream_write_value32;
+  if (!std::strcmp(name, "cuStreamWaitValue32")) *f = (void*)&fake_cuda::stream_wait_value32;
+  if (q) *q = cudaDriverEntryPointSuccess;
+  return *f ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 #endif  // FAKE_CUDA_RUNTIME_H

@@ -1,0 +1,139 @@
+"""The solver source itself -- multigridanisotropicdiffusion_b200/csrc/madgpu.cu with mad_kernels.cuh and mad_fast.cuh, UNMODIFIED --
+executed on the CPU and compared with the oracle.  tests/mad_host/madgpu_host.cpp compiles it for the host: every CUDA thread of a
+block is a fibre, switched at __syncthreads / warp shuffles / named barriers (tests/mad_host/fiber_shim.h), the CUDA runtime is
+host memory (tests/fake_cuda/).  The product's own Python binding (MadSolver) is pointed at that build for the duration of a test,
+so these read like the GPU parity tests: hierarchy, operator evaluation, both smoothers (generic multicolour kernels and the
+streaming kernels with packed fp16 rows), residuals, transfers, coarse solve, V-cycle / FMG drivers, the output casts.
+
+A check of the code, not a CPU path of the product: libmadgpu.so still refuses to run without a GPU (tests/test_cpu_host.py).
+Volumes are tiny on purpose (a fibre switch costs ~1 us); their coarsest grids stay below the 2048 unknowns of the dense inverse."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from util import ROOT, random_image, random_spd_tensor, rel_l2
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "mad_host"))
+import hostlib  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def host():
+    return hostlib.load()
+
+
+@pytest.fixture
+def MadSolver(host, monkeypatch):
+    from multigridanisotropicdiffusion_b200 import _lib as B
+    from multigridanisotropicdiffusion_b200 import solver
+    monkeypatch.setattr(B, "_lib", host)
+    return solver.MadSolver
+
+
+@pytest.mark.parametrize("shape,sp", [((33, 48), (0.7, 1.3)), ((13, 12, 15), (1.0, 0.5, 2.0))])
+@pytest.mark.parametrize("smoother", ["wj", "gs"])
+def test_generic_kernels_solve_matches_oracle(MadSolver, shape, sp, smoother):
+    """2-D and 3-D, vertex and cell centring, cross terms: the kernels of mad_kernels.cuh through whole solves."""
+    sm = 1 if smoother == "wj" else 0
+    T, img = random_spd_tensor(shape, seed=2), random_image(shape, seed=5)
+    with MadSolver(shape, sp, time_step=0.1, smoother=sm, iterations_per_grid=2, tolerance=1e-9, max_cycles=40, number_of_steps=2) as s:
+        s.set_tensor(T)
+        out = s.solve(img, out_dtype=np.float64)
+        st = s.last_stats
+    o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=sm, nu=2)
+    ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-9, max_cycles=40, number_of_steps=2)
+    assert max(st["final_relres"]) <= 1e-9
+    assert all(abs(a - b) <= (0 if smoother == "wj" else 2) for a, b in zip(st["cycles_per_step"], cyc))
+    assert rel_l2(out, ref) < (1e-5 if smoother == "wj" else 1e-4)  # BASELINE.json tolerances; in fact ~1e-9
+    assert rel_l2(out, ref) < 1e-7
+
+
+@pytest.mark.parametrize("smoother", ["wj", "gs"])
+def test_streaming_kernels_solve_matches_oracle(MadSolver, host, monkeypatch, smoother):
+    """The tuned kernels of mad_fast.cuh (4 voxels per thread, z-marching in registers, warp shuffles, packed fp16 operator rows for
+    Gauss-Seidel, row-pair sweep) forced onto a 64-voxel-wide volume."""
+    monkeypatch.setenv("MADGPU_FAST_MIN_NX", "8")
+    sm = 1 if smoother == "wj" else 0
+    shape, sp = (12, 16, 64), (0.3125, 0.3125, 0.5)
+    T, img = random_spd_tensor(shape, seed=2), random_image(shape, seed=5)
+    before = host.mad_host_switches()
+    with MadSolver(shape, sp, time_step=0.1, smoother=sm, iterations_per_grid=3, tolerance=1e-7, max_cycles=40) as s:
+        assert (s.gs_tile(0) is not None) == (smoother == "gs")  # the fused sweep, not one pass per colour
+        s.set_tensor(T)
+        out = s.solve(img, out_dtype=np.float64)
+        st = s.last_stats
+    assert host.mad_host_switches() - before > 10000  # the shuffles really went through the fibre scheduler
+    o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=sm, nu=3)
+    ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-7, max_cycles=40)
+    assert st["final_relres"][0] <= 1e-7 and abs(st["cycles_per_step"][0] - cyc[0]) <= (0 if smoother == "wj" else 2)
+    assert rel_l2(out, ref) < (1e-5 if smoother == "wj" else 1e-4)
+
+
+def test_operators_and_casts(MadSolver):
+    """Per-operator entry points on a mixed-centring hierarchy, FMG, smoother-only mode, integer pixels."""
+    shape, sp = (14, 25, 12), (0.33, 0.33, 0.33)
+    T = random_spd_tensor(shape, seed=2)
+    o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=1, nu=2)
+    with MadSolver(shape, sp, time_step=0.1, smoother=1, iterations_per_grid=2, tolerance=1e-9, max_cycles=30) as s:
+        s.set_tensor(T)
+        assert [l["shape"] for l in s.levels] == [l["shape"] for l in o.levels]
+        for l in range(s.nlevels):
+            np.testing.assert_allclose(np.moveaxis(s.op_get_tensor(l), 0, -1).reshape(-1), np.moveaxis(o.tensor(l), 0, -1).reshape(-1), rtol=2e-6, atol=1e-6)
+            A = s.op_assemble(l).astype(np.float64)
+            np.testing.assert_allclose(A, o.stencil(l), rtol=0, atol=2e-5 * np.abs(o.stencil(l)).max())
+            u, f = random_image(s.levels[l]["shape"], seed=l + 1), random_image(s.levels[l]["shape"], seed=l + 9)
+            assert rel_l2(s.op_smooth(l, u, f, smoother=1), o.smooth(l, u.astype(np.float64), f.astype(np.float64))) < 2e-6
+            r, nrm = s.op_residual(l, u, f)
+            ro = o.residual(l, u.astype(np.float64), f.astype(np.float64))
+            assert rel_l2(r, ro) < 2e-5 and abs(nrm - np.linalg.norm(ro)) < 1e-4 * np.linalg.norm(ro)
+        fine = random_image(shape, seed=4)
+        cent = o.levels[1]["centering"]
+        c = s.op_restrict(0, fine)
+        assert rel_l2(c, O.restrict(fine.astype(np.float64), cent)) < 1e-6
+        assert rel_l2(s.op_prolong(0, c), O.interpolate(c.astype(np.float64), cent, shape)) < 1e-6
+        fl = random_image(s.levels[-1]["shape"], seed=3)
+        assert rel_l2(s.op_coarse_solve(fl), o.direct_solve(fl.astype(np.float64))) < 1e-5
+        img = np.round(random_image(shape, seed=5) - 100.0)
+        for cycle in (s.FMG, s.SMOOTHER):
+            s.set_solver(cycle=cycle, max_cycles=12 if cycle == s.SMOOTHER else 30)
+            out = s.solve(img.astype(np.float32), out_dtype=np.float64)
+            ref, cyc, _ = o.solve(img, cycle=cycle, tolerance=1e-9, max_cycles=12 if cycle == s.SMOOTHER else 30)
+            assert abs(s.last_stats["cycles_per_step"][0] - cyc[0]) <= 1 and rel_l2(out, ref) < 1e-5
+        s.set_solver(cycle=s.VCYCLE, max_cycles=30)
+        o16 = s.solve(img.astype(np.int16))  # static_cast< short >: truncation toward zero, negative values included
+        ref, _, _ = o.solve(img, tolerance=1e-9, max_cycles=30)
+        d = np.abs(o16.astype(int) - np.trunc(ref).astype(int))
+        assert o16.dtype == np.int16 and d.max() <= 1 and (d != 0).mean() < 5e-3
+
+
+def test_contexts_release_device_memory(MadSolver, host):
+    before = host.mad_host_live_allocs()
+    shape = (12, 14, 16)
+    with MadSolver(shape, (1, 1, 1), time_step=0.1) as s:
+        s.set_tensor(random_spd_tensor(shape, seed=1))
+        s.solve(random_image(shape))
+        assert host.mad_host_live_allocs() > before
+    assert host.mad_host_live_allocs() == before
+
+
+@pytest.mark.parametrize("cycle", ["v", "fmg"])
+@pytest.mark.parametrize("smoother", ["wj", "gs"])
+@pytest.mark.parametrize("tag,shape,sp", [("small2d", (49, 33), (0.7, 1.3)), ("small3d", (23, 25, 27), (0.3125, 0.3125, 0.5))])
+def test_golden_vectors_of_the_reference_code(MadSolver, tag, shape, sp, smoother, cycle):
+    """The CUDA source against the vectors recorded from the reference's own code (tests/golden/make_golden.py): cross terms,
+    mixed vertex / cell centring, two time steps -- the same assertions as tests/test_gpu_golden.py makes on the GPU."""
+    from util import GOLDEN
+    g = np.load(os.path.join(GOLDEN, f"ref_{tag}_{smoother}_{cycle}.npz"))
+    T, img = random_spd_tensor(shape, seed=2), random_image(shape, seed=5)
+    with MadSolver(shape, sp, time_step=0.1, smoother=1 if smoother == "wj" else 0, iterations_per_grid=2, cycle=1 if cycle == "fmg" else 0,
+                   tolerance=1e-10, max_cycles=100, number_of_steps=2) as s:
+        s.set_tensor(T)
+        out = s.solve(img, out_dtype=np.float64)
+        st = s.last_stats
+    assert all(r <= 1e-10 for r in st["final_relres"][:2])
+    assert rel_l2(out, g["sample"]) < 1e-6
+    for a, b in zip(st["cycles_per_step"], g["cycles"]):
+        assert abs(a - int(b)) <= (1 if smoother == "wj" else 3)
