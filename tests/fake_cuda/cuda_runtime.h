@@ -49,15 +49,46 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->major = 
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "fake CUDA error"; }
+// "Device" allocations are poisoned (0xFF: NaN as float and double) and fenced by guard zones that are checked when the block is
+// freed: a kernel that writes outside its buffers aborts the test, one that reads outside or reads memory nobody wrote gets NaNs.
+namespace fake_cuda
+{
+constexpr size_t GUARD = 4096;
+constexpr unsigned char GUARD_BYTE = 0xA5;
+struct Header { size_t bytes; size_t magic; };
+}  // namespace fake_cuda
 inline cudaError_t cudaMalloc(void** p, size_t bytes)
 {
-  *p = std::malloc(bytes ? bytes : 1);
-  if (!*p) return cudaErrorMemoryAllocation;
-  std::memset(*p, 0xFF, bytes);  // NaN pattern for floats and doubles
-  __atomic_add_fetch(&fake_cuda::g_live_allocs, 1, __ATOMIC_RELAXED);
+  using namespace fake_cuda;
+  char* raw = static_cast<char*>(std::malloc(bytes + 2 * GUARD));
+  if (!raw) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  std::memset(raw, GUARD_BYTE, GUARD);
+  std::memset(raw + GUARD, 0xFF, bytes);
+  std::memset(raw + GUARD + bytes, GUARD_BYTE, GUARD);
+  Header h = {bytes, 0xC0DAC0DAu};
+  std::memcpy(raw, &h, sizeof h);  // the first bytes of the lower guard hold the size
+  *p = raw + GUARD;
+  __atomic_add_fetch(&g_live_allocs, 1, __ATOMIC_RELAXED);
   return cudaSuccess;
 }
-inline cudaError_t cudaFree(void* p) { if (p) { std::free(p); __atomic_sub_fetch(&fake_cuda::g_live_allocs, 1, __ATOMIC_RELAXED); } return cudaSuccess; }
+inline cudaError_t cudaFree(void* p)
+{
+  using namespace fake_cuda;
+  if (!p) return cudaSuccess;
+  char* raw = static_cast<char*>(p) - GUARD;
+  Header h;
+  std::memcpy(&h, raw, sizeof h);
+  bool ok = h.magic == 0xC0DAC0DAu;
+  for (size_t i = sizeof h; ok && i < GUARD; ++i) ok = (unsigned char)raw[i] == GUARD_BYTE;
+  for (size_t i = 0; ok && i < GUARD; ++i) ok = (unsigned char)raw[GUARD + h.bytes + i] == GUARD_BYTE;
+  if (!ok) {
+    std::fprintf(stderr, "fake_cuda: a guard zone of the %zu-byte allocation %p was overwritten (out-of-bounds write)\n", h.magic == 0xC0DAC0DAu ? h.bytes : 0, p);
+    std::abort();
+  }
+  std::free(raw);
+  __atomic_sub_fetch(&g_live_allocs, 1, __ATOMIC_RELAXED);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, bytes); return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new FakeStream(); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }

@@ -306,6 +306,13 @@ T shuffle(T v, int src)
     mad_host::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { MAD_UNPAREN kernel(__VA_ARGS__); });                     \
   } while (0)
 
+// csrc/ved_kernels.cuh launches through VED_LAUNCH (no dynamic shared memory)
+#define VED_LAUNCH(kernel, grid, block, stream, ...)                                                                        \
+  do {                                                                                                                      \
+    if (mad_host::trace()) std::fprintf(stderr, "mad_host: launch %s\n", #kernel);                                          \
+    mad_host::launch(dim3(grid), dim3(block), 0, [&] { kernel(__VA_ARGS__); });                                             \
+  } while (0)
+
 inline void __syncthreads() { mad_host::sync_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { mad_host::sync_warp(); }
 inline void __threadfence_block() {}

@@ -137,3 +137,68 @@ def test_golden_vectors_of_the_reference_code(MadSolver, tag, shape, sp, smoothe
     assert rel_l2(out, g["sample"]) < 1e-6
     for a, b in zip(st["cycles_per_step"], g["cycles"]):
         assert abs(a - int(b)) <= (1 if smoother == "wj" else 3)
+
+
+# ---- the VED filter end to end: front-end kernels + the real solver, both from the product's CUDA source ------------------------
+def _ved_sub_volume():
+    from util import load_ved_test
+    img, sp = load_ved_test()
+    return np.ascontiguousarray(img[20:44, 24:52, 18:48]), sp  # (24, 28, 30) around vessels
+
+
+@pytest.mark.parametrize("pixel,smoother,cycle", [(np.int16, "gs", 0), (np.float64, "wj", 1)])
+def test_whole_ved_filter_on_the_emulated_device(host, monkeypatch, pixel, smoother, cycle):
+    """VEDMultigridImageFilter.Update() -- madved_run: Hessians, vesselness, tensor handed to the solver in "device" memory
+    (madgpu_set_tensor_device_f32), DiffusionStep in place (madgpu_solve_device_f32), output cast from the fp64 iterate
+    (madgpu_fetch_output) -- against the oracle's GenerateData, with the parameters of test/itkVEDTest_GS.cxx."""
+    from multigridanisotropicdiffusion_b200 import _lib as B
+    import multigridanisotropicdiffusion_b200 as M
+    from oracle import ved as V
+    monkeypatch.setattr(B, "_lib", host)
+    img, sp = _ved_sub_volume()
+    img = img.astype(pixel)
+    f = M.VEDMultigridImageFilter(smoother)
+    f.SetCycle(cycle)
+    f.SetDiffusionIterationsPerGrid(3)
+    f.SetInput(img, sp)
+    f.SetScales([0.300, 0.482, 0.775, 1.245, 2.000])
+    f.SetAlpha(0.5); f.SetBeta(0.5); f.SetGamma(5.0); f.SetEpsilon(0.01); f.SetSensitivity(10.0)
+    f.SetIterations(2)
+    f.SetTolerance(1e-9)
+    f.SetTimeStep(0.1)
+    f.SetDiffusionIterations(2)
+    f.SetOmega(1.5)
+    f.Update()
+    out = f.GetOutput()
+    assert out.dtype == pixel and f.ved_stats["scales"] == 10 and f.stats["steps"] == 2 and max(f.stats["final_relres"]) <= 1e-9
+    want, info = V.ved_filter(img, sp, V.DEFAULT_SCALES, alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=1.5, sensitivity=10.0, iterations=2,
+                              diffusion_iterations=2, smoother=0 if smoother == "gs" else 1, cycle=cycle, time_step=0.1, tolerance=1e-9,
+                              iterations_per_grid=3, out_dtype=pixel)
+    if pixel == np.int16:
+        d = np.abs(out.astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 1e-3
+    else:
+        assert rel_l2(out, want) < 1e-6
+    assert host.mad_host_live_allocs() == 0
+
+
+def test_fetch_output_casts(MadSolver):
+    """madgpu_fetch_output: the current fp64 iterate cast to every pixel type (…Filter.hxx:267-284), after a device-buffer solve."""
+    import ctypes as C
+    from multigridanisotropicdiffusion_b200 import _lib as B
+    shape = (12, 14, 16)
+    img = np.round(random_image(shape, seed=5) - 60.0).astype(np.float32)
+    with MadSolver(shape, (1, 1, 1), time_step=0.1, tolerance=1e-9) as s:
+        s.set_tensor(random_spd_tensor(shape, seed=1))
+        ref = s.solve(img, out_dtype=np.float64)
+        work = img.copy()  # "device" memory of the host build is host memory
+        s.solve_device(work.ctypes.data, work.ctypes.data)
+        np.testing.assert_array_equal(work, ref.astype(np.float32))
+        for dt, code in ((np.float64, B.PIX_F64), (np.float32, B.PIX_F32), (np.int16, B.PIX_I16), (np.uint8, B.PIX_U8)):
+            out = np.empty(shape, dtype=dt)
+            assert s._lib.madgpu_fetch_output(s._ctx, code, C.c_void_p(out.ctypes.data)) == 0
+            if dt == np.uint8:
+                pos = ref >= 0
+                np.testing.assert_array_equal(out[pos], np.trunc(ref[pos]).astype(np.uint8))
+            else:
+                np.testing.assert_array_equal(out, np.trunc(ref).astype(dt) if dt == np.int16 else ref.astype(dt))

@@ -36,7 +36,7 @@ def host():
     out = os.path.join(ROOT, "tests", "_build", "libvedhost.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-o", out, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-fno-gnu-unique", "-o", out, src])
     L = C.CDLL(out)
     L.vh_rg_setup.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _dp]
     L.vh_rg_line.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_double]

@@ -32,7 +32,7 @@ def hostlib():
     from oracle import oracle as O
     O.build()
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-x", "c++",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-fno-gnu-unique", "-x", "c++",
                                "-I" + os.path.join(ROOT, "tests", "fake_cuda"), "-I" + os.path.join(ROOT, "tests"), "-o", out, src,
                                "-L" + os.path.join(ROOT, "oracle"), "-lmadoracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     from multigridanisotropicdiffusion_b200 import _lib as B
