@@ -7,7 +7,9 @@ registers them: 3 programs x {v, fmg, s} = its nine CTest entries.  Nothing of t
 The programs read test_data/lena.jpg and test_data/ved_test.mhd relative to the working directory and assert nothing themselves
 (SURVEY section 4); here their outputs are compared with the vectors recorded from the reference's own code.  The stand-in reader
 serves lena.jpg through a MetaImage side-car (no JPEG library in this image).
-CPU: the programs compile, link, read their inputs and -- no CPU fallback -- stop at madgpu_create.  GPU: all nine entries."""
+CPU: the programs compile, link, read their inputs and -- no CPU fallback -- stop at madgpu_create; and the same binary is run
+against the EMULATED device (LD_LIBRARY_PATH pointing at the host build of the CUDA source, tests/mad_host/), which checks the whole
+chain -- reader stand-in, drop-in header, C-ABI, kernels, output cast, writer -- on the CPU.  GPU: all nine entries."""
 import os
 import subprocess
 
@@ -40,8 +42,20 @@ def workdir(tmp_path):
     return tmp_path
 
 
-def _run(exe, cwd, test, mode):
-    return subprocess.run([exe, test, mode], cwd=str(cwd), capture_output=True, text=True, timeout=1200)
+def _run(exe, cwd, test, mode, env=None):
+    return subprocess.run([exe, test, mode], cwd=str(cwd), capture_output=True, text=True, timeout=2400, env=env)
+
+
+@pytest.fixture(scope="module")
+def emulated_env(tmp_path_factory):
+    """Environment in which `libmadgpu.so` resolves to the host build of the CUDA source (the binary's RUNPATH comes after
+    LD_LIBRARY_PATH)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mad_host"))
+    import hostlib
+    d = tmp_path_factory.mktemp("emulated_device")
+    os.symlink(hostlib.build(), str(d / "libmadgpu.so"))
+    return dict(os.environ, LD_LIBRARY_PATH=str(d) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
 
 
 def test_reference_test_programs_build_against_the_dropin_and_need_a_gpu(exe, workdir):
@@ -86,3 +100,43 @@ def test_itkVEDTest_GS(exe, workdir, mode):
         g = np.load(os.path.join(GOLDEN, "ref_vedfilter_gs_v.npz"))
         d = np.abs(out.astype(int) - g["out_short"].astype(int))
         assert d.max() <= 1 and (d != 0).mean() < 1e-3
+
+
+# ---- the same binary on the emulated device (CPU) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("smoother,mode", [("WJ", "v"), ("GS", "fmg")])
+def test_itk2DDiffusionTest_on_the_emulated_device(exe, workdir, emulated_env, smoother, mode):
+    r = _run(exe, workdir, f"itk2DDiffusionTest_{smoother}", mode, env=emulated_env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out, _ = metaimage.read(str(workdir / "test_data" / "lena_out.jpg.mhd"))
+    g = np.load(os.path.join(GOLDEN, f"ref_lena_{smoother.lower()}_{mode}.npz"))
+    sub = int(g["sub"])
+    d = np.abs(out[::sub, ::sub].astype(int) - g["sample"].astype(np.float32).astype(np.uint8).astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 0.005
+    cycles = r.stdout.count("|--- VCycle n.")
+    assert abs(cycles - int(g["cycles"][0])) <= (1 if smoother == "WJ" else 3)
+
+
+def test_itkVEDTest_GS_on_the_emulated_device(exe, tmp_path, emulated_env):
+    """itkVEDTest_GS v.  By default on a 32x40x64 crop of ved_test.mhd against the oracle's GenerateData (about 20 s); with
+    MADGPU_FULL_EMULATION=1 on the whole volume against the vector recorded from the reference's own code (about 90 s; the result
+    of that run is identical to the golden vector in every voxel)."""
+    from oracle import ved as V
+    full = os.environ.get("MADGPU_FULL_EMULATION") == "1"
+    vol, sp = load_ved_test()
+    if not full:
+        vol = np.ascontiguousarray(vol[18:50, 20:60, 2:66])
+    d = tmp_path / "test_data"
+    d.mkdir()
+    metaimage.write(str(d / "ved_test.mhd"), vol, {"spacing": sp, "TransformMatrix": "-1 0 0 0 -1 0 0 0 1"})
+    r = _run(exe, tmp_path, "itkVEDTest_GS", "v", env=emulated_env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out, meta = metaimage.read(str(d / "ved_test_out.mhd"))
+    assert out.dtype == np.int16 and out.shape == vol.shape and meta["spacing"] == sp
+    if full:
+        want = np.load(os.path.join(GOLDEN, "ref_vedfilter_gs_v.npz"))["out_short"]
+    else:
+        want, _ = V.ved_filter(vol, sp, V.DEFAULT_SCALES, alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=1.5, sensitivity=10.0, iterations=1,
+                               diffusion_iterations=4, smoother=0, cycle=0, time_step=0.1, tolerance=1e-10, iterations_per_grid=3, out_dtype=np.int16)
+    dd = np.abs(out.astype(int) - want.astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3
+    assert np.abs(out.astype(int) - vol.astype(int)).max() > 5
