@@ -10,6 +10,22 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    if os.environ.get("MADGPU_EMULATED_DEVICE") == "1":
+        _bind_emulated_device()
+
+
+def _bind_emulated_device():
+    """MADGPU_EMULATED_DEVICE=1 python -m pytest tests/test_gpu_ved.py -m gpu ...: dry-run GPU test files on the CPU.  The
+    product's Python binding (and, through LD_LIBRARY_PATH, the C++ drop-in test programs) is pointed at the host build of the CUDA
+    source (tests/mad_host/), so the TEST CODE can be checked before it is spent on a GPU box.  Slow, and never a substitute for the
+    GPU run: the driver's `-m gpu` run does not set this variable."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mad_host"))
+    import hostlib
+    hostlib.bind(hostlib.load())
+    d = tempfile.mkdtemp(prefix="madgpu_emulated_")
+    os.symlink(hostlib.HOST_LIB, os.path.join(d, "libmadgpu.so"))
+    os.environ["LD_LIBRARY_PATH"] = d + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")
 
 
 @pytest.fixture(scope="session")
