@@ -419,14 +419,15 @@ __device__ __forceinline__ void zero_uplane(UPlane<T>& P)
 }
 
 // sum over the off-diagonal entries at slot j (apply_offdiag of mad_kernels.cuh on registers)
-template <typename T>
-__device__ __forceinline__ T offdiag(const Coef<T>& c, const UPlane<T>& m, const UPlane<T>& q, const UPlane<T>& n, int j)
+// CT: the type the coefficients were evaluated in (T, or float under a double accumulation: MODE_RES_C32)
+template <typename T, typename CT>
+__device__ __forceinline__ T offdiag(const Coef<CT>& c, const UPlane<T>& m, const UPlane<T>& q, const UPlane<T>& n, int j)
 {
-  T s = c.xp[j] * q.r[1].v[j + 2] + c.xm[j] * q.r[1].v[j] + c.yp[j] * q.r[2].v[j + 1] + c.ym[j] * q.r[0].v[j + 1];
-  s += c.exy[j] * ((q.r[2].v[j + 2] - q.r[0].v[j + 2]) - (q.r[2].v[j] - q.r[0].v[j]));
-  s += c.zp[j] * n.r[1].v[j + 1] + c.zm[j] * m.r[1].v[j + 1];
-  s += c.exz[j] * ((n.r[1].v[j + 2] - m.r[1].v[j + 2]) - (n.r[1].v[j] - m.r[1].v[j]));
-  s += c.eyz[j] * ((n.r[2].v[j + 1] - m.r[2].v[j + 1]) - (n.r[0].v[j + 1] - m.r[0].v[j + 1]));
+  T s = T(c.xp[j]) * q.r[1].v[j + 2] + T(c.xm[j]) * q.r[1].v[j] + T(c.yp[j]) * q.r[2].v[j + 1] + T(c.ym[j]) * q.r[0].v[j + 1];
+  s += T(c.exy[j]) * ((q.r[2].v[j + 2] - q.r[0].v[j + 2]) - (q.r[2].v[j] - q.r[0].v[j]));
+  s += T(c.zp[j]) * n.r[1].v[j + 1] + T(c.zm[j]) * m.r[1].v[j + 1];
+  s += T(c.exz[j]) * ((n.r[1].v[j + 2] - m.r[1].v[j + 2]) - (n.r[1].v[j] - m.r[1].v[j]));
+  s += T(c.eyz[j]) * ((n.r[2].v[j + 1] - m.r[2].v[j + 1]) - (n.r[0].v[j + 1] - m.r[0].v[j + 1]));
   return s;
 }
 
@@ -454,7 +455,9 @@ __device__ __forceinline__ StepRaw<UT, FT> issue_step(const Geom& g, const Tenso
   return R;
 }
 
-enum { MODE_WJ = 0, MODE_RES = 1, MODE_COEF = 2 };
+// MODE_RES_C32: MODE_RES with the operator row evaluated in fp32 (exactly the row the fp32 sweeps use) and applied in T -- for the
+// fp64 stop-test residual, whose fp64 row evaluation (conversions + FP64 pipe) is what bounds it; opt-in, MADGPU_RES64_COEF32=1
+enum { MODE_WJ = 0, MODE_RES = 1, MODE_COEF = 2, MODE_RES_C32 = 3 };
 
 // Packed operator rows for the Gauss-Seidel smoother: per group of four x-voxels ten fp16 values per voxel, 80 bytes =
 // five 16-byte words; word i holds entries 2i and 2i+1, each for the four voxels.  Entries: 0 1/diag, then the
@@ -472,6 +475,8 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
                                                          OT* __restrict__ out, double* __restrict__ partials, float omega, int zc, int pfd, int uzero)
 {
   // uzero: the iterate is identically zero (first sweep of a V-cycle leg): `u` is not read
+  constexpr bool RES = MODE == MODE_RES || MODE == MODE_RES_C32;
+  typedef typename std::conditional<MODE == MODE_RES_C32, float, T>::type CT;  // type the row is evaluated in
   const Pos p = make_pos(g);
   const bool valid = p.y < g.ny;
   double sq = 0.0;
@@ -510,8 +515,8 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
       const V4<T> fv = finish4<T>(R.f);
       // ---- issue every load of the next plane step before doing any arithmetic ----
       if (PF && z + 1 < z1) R = issue_step<UT, FT>(g, D, u, f, p, rowo, z + 1);
-      Coef<T> c;
-      coefficients<T>(g, D, p, z, oc, S, F, c);
+      Coef<CT> c;
+      coefficients<CT>(g, D, p, z, oc, S, F, c);
       float res[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 4 && MODE != MODE_COEF; ++j) {
@@ -519,9 +524,9 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
         const T uj = uc.r[1].v[j + 1];
         if (MODE == MODE_WJ) {
           // mad/itkMultigridWeightedJacobiSmoother.hxx:88-89
-          res[j] = float((fv.v[j] - s) * fast_div(om, c.diag[j]) + om1 * uj);
+          res[j] = float((fv.v[j] - s) * fast_div(om, T(c.diag[j])) + om1 * uj);
         } else {
-          const T r = fv.v[j] - c.diag[j] * uj - s;
+          const T r = fv.v[j] - T(c.diag[j]) * uj - s;
           res[j] = float(r);
           if (p.xt + j < g.nx) sq += (double)r * (double)r;
         }
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
       S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
     }
   }
-  if (MODE == MODE_RES && partials) {
+  if (RES && partials) {
     const double t = block_sum(sq);
     if (threadIdx.x == 0 && threadIdx.y == 0)
       partials[(size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)] = t;

@@ -134,6 +134,7 @@ struct madgpu_ctx {
   int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
+  int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 (opt-in tuning hook, MADGPU_RES64_COEF32)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
 };
 
@@ -626,7 +627,8 @@ void op_residual64(madgpu_ctx* ctx, float* r32_or_null, double* r64_or_null)
     if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, double, double, double, double>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
     else MAD_LAUNCH((k_residual<2, double, double, double, double>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
   } else if (use_fast(ctx, L)) {
-    const size_t nb = launch_fast<fast::MODE_RES, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f);
+    const size_t nb = ctx->res64_c32 ? launch_fast<fast::MODE_RES_C32, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f)
+                                     : launch_fast<fast::MODE_RES, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f);
     reduce_partials(ctx, nb);
     return;
   } else {
@@ -1334,6 +1336,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->gs_coef16 = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_FUSED");
     ctx->gs_fused = e ? atoi(e) : 1;
+    e = getenv("MADGPU_RES64_COEF32");
+    ctx->res64_c32 = e ? atoi(e) : 0;
     e = getenv("MADGPU_FAST_CFG");
     ctx->fast_cfg = e ? atoi(e) : 0;
   }

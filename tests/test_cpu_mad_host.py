@@ -212,3 +212,33 @@ def test_gpu_operator_tests_on_the_emulated_device():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_ops.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
                        capture_output=True, text=True, env=env, cwd=ROOT, timeout=1200)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("smoother", ["wj", "gs"])
+def test_fp64_residual_with_fp32_operator_rows(MadSolver, monkeypatch, smoother):
+    """MADGPU_RES64_COEF32=1 (opt-in, k_fast_sweep<MODE_RES_C32>): the level-0 stop-test residual applies, in fp64, the operator
+    row evaluated in fp32 -- the row the fp32 sweeps use -- instead of re-evaluating it in fp64.  The residual of an arbitrary
+    iterate then differs from the fp64-row residual by the rounding of the row (~1e-7 relative to |A||u|), the converged image by
+    about as much, cycle counts not at all."""
+    monkeypatch.setenv("MADGPU_FAST_MIN_NX", "8")
+    sm = 1 if smoother == "wj" else 0
+    shape, sp = (12, 16, 64), (0.3125, 0.3125, 0.5)
+    T, img = random_spd_tensor(shape, seed=2), random_image(shape, seed=5)
+    o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=sm, nu=3)
+    ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-9, max_cycles=40)
+    u, f = random_image(shape, seed=3).astype(np.float64), random_image(shape, seed=4).astype(np.float64)
+    r_o = o.residual(0, u, f)
+    scale = np.abs(u).max() * np.abs(o.stencil(0)).sum(-1).max()
+    res, outs, cycles = {}, {}, {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MADGPU_RES64_COEF32", flag)
+        with MadSolver(shape, sp, time_step=0.1, smoother=sm, iterations_per_grid=3, tolerance=1e-9, max_cycles=40) as s:
+            s.set_tensor(T)
+            res[flag], nrm = s.op_residual_f64(u, f, norm_only=False)
+            _, nrm_fast = s.op_residual_f64(u, f, norm_only=True)  # the streaming kernel of the solve loop
+            assert abs(nrm_fast - np.linalg.norm(r_o)) < (1e-12 if flag == "0" else 3e-7) * np.linalg.norm(r_o) * (1 if flag == "0" else scale / np.linalg.norm(r_o) * np.sqrt(u.size))
+            outs[flag] = s.solve(img, out_dtype=np.float64)
+            cycles[flag] = s.last_stats["cycles_per_step"]
+            assert s.last_stats["final_relres"][0] <= 1e-9
+    assert cycles["0"] == cycles["1"] and abs(cycles["1"][0] - cyc[0]) <= (0 if smoother == "wj" else 2)
+    assert rel_l2(outs["1"], outs["0"]) < 5e-7 and rel_l2(outs["1"], ref) < 1e-6
