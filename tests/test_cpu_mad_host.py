@@ -204,14 +204,24 @@ def test_fetch_output_casts(MadSolver):
                 np.testing.assert_array_equal(out, np.trunc(ref).astype(dt) if dt == np.int16 else ref.astype(dt))
 
 
+def _run_gpu_tests_on_the_emulated_device(*pytest_args):
+    import subprocess
+    env = dict(os.environ, MADGPU_EMULATED_DEVICE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", *pytest_args, "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"], capture_output=True,
+                       text=True, env=env, cwd=ROOT, timeout=1800)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_gpu_operator_tests_on_the_emulated_device():
     """tests/test_gpu_ops.py -- the per-operator GPU parity tests, green on a B200 -- run unchanged against the host build of the
     CUDA source (MADGPU_EMULATED_DEVICE=1, tests/conftest.py): the emulation and the GPU agree on what passes."""
-    import subprocess
-    env = dict(os.environ, MADGPU_EMULATED_DEVICE="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_ops.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
-                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=1200)
-    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    _run_gpu_tests_on_the_emulated_device(os.path.join(ROOT, "tests", "test_gpu_ops.py"))
+
+
+def test_gpu_edge_case_tests_on_the_emulated_device():
+    """The cheap edge cases of tests/test_gpu_solve.py: error paths, a single-level volume, a zero right-hand side, every output
+    pixel cast.  (The whole file passes on the emulation too, in about a quarter of an hour.)"""
+    _run_gpu_tests_on_the_emulated_device(os.path.join(ROOT, "tests", "test_gpu_solve.py"), "-k", "error_paths or single_level or pixel_casts")
 
 
 @pytest.mark.parametrize("smoother", ["wj", "gs"])
