@@ -279,7 +279,7 @@ def run_ours(args):
     import numpy as np
     import torch
 
-    from multigridanisotropicdiffusion_b200 import MadSolver, phantom
+    from multigridanisotropicdiffusion_b200 import MadGpuError, MadSolver, phantom
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -309,12 +309,35 @@ def run_ours(args):
         z0, z1 = slabs.slab_range(n, rank, world)
         img, D = phantom.vessel_phantom(shape, device=dev, z_range=(z0, z1))
         torch.cuda.synchronize()
-        s = MadSolver(shape, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, tolerance=0.0,
-                      max_cycles=1 << 20, device=local_rank, rank=rank, world_size=world, nccl_id=slabs.create_unique_id())
         # peer-memory halo (NVLink stores from the producing kernels): verified on 2 and 4 GPUs; an 8-rank run hung in this
         # round and could not be diagnosed before the GPU budget ran out, so beyond 4 ranks NCCL send/recv stays the default
         want_peer = args.peer_halo or (not args.nccl_halo and world <= 4)
+        if want_peer and world > 4:
+            # beyond the rank counts verified on hardware: arrival counters awaited by the bounded k_halo_wait, so that a signal that
+            # never arrives costs a time-out and an error on every rank (handled below) instead of a hung stream
+            os.environ["MADGPU_P2P_WAIT"] = "kernel"
+            os.environ.setdefault("MADGPU_P2P_TIMEOUT_MS", "3000")
+
+        def make_slab_solver():
+            return MadSolver(shape_global, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, tolerance=0.0,
+                             max_cycles=1 << 20, device=local_rank, rank=rank, world_size=world, nccl_id=slabs.create_unique_id())
+
+        shape_global = shape
+        s = make_slab_solver()
         peer_halo = want_peer and slabs.enable_peer_halo(s)
+        if peer_halo and world > 4:
+            # trial cycles: a time-out is reported by every rank in the same cycle (the flag travels with the norm all-reduce)
+            try:
+                s.set_tensor_device([D[c].data_ptr() for c in range(6)])
+                s.cycles_begin(d_in=img.data_ptr())
+                s.cycles_run(2)
+            except MadGpuError as e:
+                if rank == 0:
+                    print(f"bench.py: peer-memory halo failed on {world} ranks ({e}); falling back to the NCCL halo", file=sys.stderr, flush=True)
+                s.close()
+                os.environ["MADGPU_P2P_WAIT"] = "memop"
+                s = make_slab_solver()
+                peer_halo = False
     else:
         img, D = phantom.vessel_phantom(shape, device=dev)
         torch.cuda.synchronize()

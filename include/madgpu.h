@@ -132,7 +132,10 @@ int madgpu_create_slab(const madgpu_params *p, const void *nccl_unique_id, madgp
 int madgpu_ipc_export(madgpu_ctx *ctx, void *blob, size_t capacity, size_t *needed);
 int madgpu_ipc_import(madgpu_ctx *ctx, const void *blob_lower, const void *blob_upper);
 /* import ends with a handshake with both neighbours and fails (MADGPU_ECUDA) when it does not complete; the ranks must then
- * agree: if any rank failed, all call madgpu_ipc_disable and the NCCL exchange stays in use. */
+ * agree: if any rank failed, all call madgpu_ipc_disable and the NCCL exchange stays in use.
+ * Environment: MADGPU_P2P_WAIT=kernel awaits the arrival counters with a bounded one-thread kernel (MADGPU_P2P_TIMEOUT_MS, default
+ * 10000) instead of cuStreamWaitValue32: a signal that never arrives then makes the running solve / cycles call fail with
+ * MADGPU_ECUDA on every rank in the same cycle (the context must be recreated) instead of hanging the stream. */
 int madgpu_ipc_disable(madgpu_ctx *ctx);
 /* planes [z_begin, z_begin + z_count) of `level` held by this context; global_nz = planes of the whole level.
  * Valid for the levels this context holds (all of them when world_size == 1). */

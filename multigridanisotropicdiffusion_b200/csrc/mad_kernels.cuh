@@ -281,6 +281,28 @@ __global__ void __launch_bounds__(512) k_sumsq(Geom g, const FT* __restrict__ f,
     partials[(size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)] = t;
 }
 
+// Peer-memory halo, bounded wait (MADGPU_P2P_WAIT=kernel): one thread polls this rank's two arrival counters until both have
+// reached the wanted sequence numbers (cyclic compare, as cuStreamWaitValue32's GEQ) or `timeout_cycles` have passed.  A time-out
+// does not stop the stream -- the kernels behind it run on stale ghost planes -- but it is recorded: fail[0] = 1 travels with the
+// next residual-norm all-reduce to every rank, diag = {wanted lower, wanted upper, seen lower, seen upper}.
+__global__ void k_halo_wait(const volatile unsigned* flags, unsigned need_lo, unsigned need_hi, int has_lo, int has_hi, long long timeout_cycles,
+                            double* fail, unsigned* diag)
+{
+  if (fail[0] != 0.0) return;  // an earlier wait of this cycle already timed out: do not pay the time-out again
+  const long long t0 = clock64();
+  bool ok_lo = !has_lo, ok_hi = !has_hi;
+  unsigned seen_lo = 0, seen_hi = 0;
+  while (!(ok_lo && ok_hi)) {
+    if (!ok_lo) { seen_lo = flags[0]; ok_lo = (int)(seen_lo - need_lo) >= 0; }
+    if (!ok_hi) { seen_hi = flags[1]; ok_hi = (int)(seen_hi - need_hi) >= 0; }
+    if (clock64() - t0 > timeout_cycles) break;
+  }
+  if (!(ok_lo && ok_hi)) {
+    fail[0] = 1.0;
+    diag[0] = need_lo; diag[1] = need_hi; diag[2] = seen_lo; diag[3] = seen_hi;
+  }
+}
+
 // out[0] = sum(partials[0..n)) in a fixed order (one block).
 __global__ void __launch_bounds__(1024) k_reduce_partials(const double* __restrict__ partials, long long n, double* __restrict__ out)
 {

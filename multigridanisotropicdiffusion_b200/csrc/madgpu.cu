@@ -120,6 +120,9 @@ struct madgpu_ctx {
   uint32_t* flags_hi;     // the upper neighbour's flags (mapped), we write [0]
   uint32_t halo_seq;      // number of fields produced so far (identical on every rank: same program order)
   bool p2p;
+  int p2p_wait_kernel;          // MADGPU_P2P_WAIT=kernel: arrival counters are awaited by k_halo_wait (bounded) instead of cuStreamWaitValue32
+  long long p2p_timeout_cycles; // MADGPU_P2P_TIMEOUT_MS (default 10 s at ~2 GHz)
+  int p2p_drop_rank, p2p_drop_seq;  // test hook MADGPU_P2P_TEST_DROP_SIGNAL=rank:seq: from that sequence number on the rank's signals are not sent
   int rank, world;
   std::string sticky;  // first collective error inside an operator
   bool borrowed_stream;  // sub-context of a slab context: runs on the parent's stream
@@ -366,6 +369,7 @@ void halo_signal(madgpu_ctx* ctx, const void* field)
   madgpu_ctx::Shared* s = shared_of(ctx, field);
   if (!s) return;
   s->produced = ++ctx->halo_seq;
+  if (ctx->rank == ctx->p2p_drop_rank && ctx->p2p_drop_seq >= 0 && (int)s->produced >= ctx->p2p_drop_seq) return;  // test hook: this rank's signals stop arriving
   if (ctx->flags_lo) latch(ctx, g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_lo + 1), s->produced, 0), "cuStreamWriteValue32");
   if (ctx->flags_hi) latch(ctx, g_write_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags_hi + 0), s->produced, 0), "cuStreamWriteValue32");
 }
@@ -384,6 +388,12 @@ bool halo_wait(madgpu_ctx* ctx, const void* field)
   if (!ctx->p2p) return false;
   madgpu_ctx::Shared* s = shared_of(ctx, field);
   if (!s || s->produced == 0) return false;
+  if (ctx->p2p_wait_kernel) {  // bounded wait: a lost signal costs a time-out and an error, not a hung stream
+    MAD_LAUNCH((k_halo_wait), 1, 1, 0, ctx->stream, (const volatile unsigned*)ctx->flags, s->produced, s->produced, ctx->flags_lo != nullptr,
+               ctx->flags_hi != nullptr, ctx->p2p_timeout_cycles, ctx->d_scalar + 1, (unsigned*)ctx->flags + 8);
+    ctx->launches++;
+    return true;
+  }
   const unsigned int GEQ = 1;  // CU_STREAM_WAIT_VALUE_GEQ
   if (ctx->flags_lo) latch(ctx, g_wait_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags + 0), s->produced, GEQ), "cuStreamWaitValue32");
   if (ctx->flags_hi) latch(ctx, g_wait_value(ctx->stream, (unsigned long long)(uintptr_t)(ctx->flags + 1), s->produced, GEQ), "cuStreamWaitValue32");
@@ -574,8 +584,18 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
 
 double read_scalar(madgpu_ctx* ctx)
 {
-  cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  const bool watch = ctx->p2p && ctx->p2p_wait_kernel;  // d_scalar[1]: "a halo wait timed out on some rank" (all-reduced with the norm)
+  cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, (watch ? 2 : 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
+  if (watch && ctx->h_scalar[1] != 0.0) {
+    unsigned d[4] = {0, 0, 0, 0};
+    cudaMemcpy(d, ctx->flags + 8, sizeof d, cudaMemcpyDeviceToHost);
+    char msg[256];
+    snprintf(msg, sizeof msg, "peer-memory halo: an arrival-counter wait timed out on %d rank(s); rank %d last wanted %u / %u from its lower / upper "
+             "neighbour and saw %u / %u -- results are invalid, the context must be recreated (NCCL halo)", (int)ctx->h_scalar[1], ctx->rank, d[0], d[1], d[2], d[3]);
+    if (ctx->sticky.empty()) ctx->sticky = msg;
+    ctx->p2p = false;
+  }
   return *ctx->h_scalar;
 }
 
@@ -583,7 +603,7 @@ double read_scalar(madgpu_ctx* ctx)
 void reduce_partials(madgpu_ctx* ctx, size_t n)
 {
   MAD_LAUNCH((k_reduce_partials), 1, 1024, 0, ctx->stream, ctx->partials, (long long)n, ctx->d_scalar);
-  if (ctx->world > 1) NCV(g_nccl.AllReduce(ctx->d_scalar, ctx->d_scalar, 1, Nccl::Float64, Nccl::Sum, ctx->comm, ctx->stream));
+  if (ctx->world > 1) NCV(g_nccl.AllReduce(ctx->d_scalar, ctx->d_scalar, ctx->p2p && ctx->p2p_wait_kernel ? 2 : 1, Nccl::Float64, Nccl::Sum, ctx->comm, ctx->stream));
 }
 
 // L.tmp = L.f - A L.u  (fp32)
@@ -1175,6 +1195,7 @@ int run_steps(madgpu_ctx* ctx)
     do {                                                                                               // :207-246
       outer_iteration(ctx, P.cycle == MADGPU_CYCLE_SMOOTHER);
       relres = std::sqrt(read_scalar(ctx)) / rhs_norm;
+      if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());  // e.g. a halo wait timed out: every rank sees it in the same cycle
       ctx->relres_hist[(size_t)n * P.max_cycles + it] = relres;
       if (P.verbose && ctx->rank == 0) {
         if (P.cycle == MADGPU_CYCLE_SMOOTHER) printf("Smoother iteration n. %d: relative residual = %g\n", it + 1, relres);
@@ -1336,6 +1357,12 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->gs_coef16 = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_FUSED");
     ctx->gs_fused = e ? atoi(e) : 1;
+    e = getenv("MADGPU_P2P_WAIT");
+    ctx->p2p_wait_kernel = e && !strcmp(e, "kernel");
+    e = getenv("MADGPU_P2P_TIMEOUT_MS");
+    ctx->p2p_timeout_cycles = (long long)((e ? atof(e) : 10000.0) * 2.0e6);
+    ctx->p2p_drop_rank = ctx->p2p_drop_seq = -1;
+    if ((e = getenv("MADGPU_P2P_TEST_DROP_SIGNAL"))) sscanf(e, "%d:%d", &ctx->p2p_drop_rank, &ctx->p2p_drop_seq);
     e = getenv("MADGPU_RES64_COEF32");
     ctx->res64_c32 = e ? atoi(e) : 0;
     e = getenv("MADGPU_FAST_CFG");
@@ -1427,6 +1454,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
   ctx->npartials = max_blocks;
   CUB(cudaMalloc((void**)&ctx->partials, max_blocks * sizeof(double)));
   CUB(cudaMalloc((void**)&ctx->d_scalar, 8 * sizeof(double)));
+  CUB(cudaMemsetAsync(ctx->d_scalar, 0, 8 * sizeof(double), ctx->stream));
   CUB(cudaMallocHost((void**)&ctx->h_scalar, 8 * sizeof(double)));
   if (world > 1) {
     // agglomeration level: dense staging of the local slab, and on rank 0 the gathered level plus the serial
@@ -1629,6 +1657,7 @@ int madgpu_cycles_run(madgpu_ctx* ctx, int32_t n, double* relres, float* device_
   for (int i = 0; i < n; ++i) {
     outer_iteration(ctx, ctx->p.cycle == MADGPU_CYCLE_SMOOTHER);
     const double r = std::sqrt(read_scalar(ctx)) / ctx->rhs_norm;
+    if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
     if (relres) relres[i] = r;
   }
   CU(cudaEventRecord(ctx->ev_b, ctx->stream));

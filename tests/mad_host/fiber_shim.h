@@ -322,6 +322,7 @@ template <typename T> T __shfl_down_sync(unsigned, T v, unsigned d) { return mad
 template <typename T> T __shfl_xor_sync(unsigned, T v, int m) { return mad_host::shuffle(v, (int)mad_host::cur().lane ^ m); }
 template <typename T> T __ldg(const T* p) { return *p; }
 inline float __fdividef(float a, float b) { return a / b; }
+inline long long clock64() { return 2 * std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }  // ~2 GHz
 using std::max;
 using std::min;
 namespace mad { namespace fast {

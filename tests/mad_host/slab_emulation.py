@@ -32,11 +32,17 @@ def main():
     ap.add_argument("--cycle", default="v", choices=["v", "fmg"])
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--nu", type=int, default=2)
+    ap.add_argument("--wait", default="memop", choices=["memop", "kernel"], help="peer halo: cuStreamWaitValue32 or the bounded k_halo_wait")
+    ap.add_argument("--drop", default="", help="rank:seq -- from that sequence number on the rank's arrival signals are not sent (needs --wait kernel); every rank must report the time-out")
     a = ap.parse_args()
     import hostlib
     os.environ["MADGPU_NCCL_LIB"] = hostlib.FAKE_NCCL
     os.environ["MADGPU_FAST_MIN_NX"] = "8"  # streaming kernels on these narrow volumes (the peer halo needs them)
     os.environ["MADGPU_AGGLOMERATE_VOXELS"] = str(a.agglomerate_voxels)
+    os.environ["MADGPU_P2P_WAIT"] = a.wait
+    os.environ["MADGPU_P2P_TIMEOUT_MS"] = "400"
+    if a.drop:
+        os.environ["MADGPU_P2P_TEST_DROP_SIGNAL"] = a.drop
     L = hostlib.load()
     hostlib.bind(L)
     from multigridanisotropicdiffusion_b200 import MadSolver, slabs
@@ -69,7 +75,8 @@ def main():
             s.close()
         except Exception as e:  # noqa: BLE001
             errs.append((r, repr(e)))
-            bar.abort()
+            if not a.drop:
+                bar.abort()
 
     single = {}
 
@@ -88,6 +95,11 @@ def main():
     [t.join() for t in th]
     print(f"slabs done after {time.time() - t0:.1f}s", flush=True)
     ts.join()
+    if a.drop:  # a lost signal: nobody hangs, every rank returns the same error
+        ok = len(errs) == world and all("timed out" in e for _, e in errs)
+        print("ERRORS", sorted(errs)[:2], flush=True)
+        print("SLAB_EMULATION_TIMEOUT_REPORTED" if ok else "SLAB_EMULATION_FAILED", flush=True)
+        return 0 if ok else 1
     if errs:
         print("ERRORS", errs, flush=True)
         return 1

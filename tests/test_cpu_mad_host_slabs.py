@@ -53,3 +53,18 @@ def test_eight_ranks_weighted_jacobi():
 
 def test_fmg_on_eight_slabs_nccl():
     _run("--world", "8", "--peer", "0", "--agglomerate-voxels", "1000", "--cycle", "fmg", "--smoother", "wj")
+
+
+def test_bounded_kernel_wait_eight_ranks():
+    """MADGPU_P2P_WAIT=kernel: the arrival counters are awaited by k_halo_wait (bounded) instead of cuStreamWaitValue32."""
+    _run("--world", "8", "--peer", "1", "--agglomerate-voxels", "1000", "--wait", "kernel", "--smoother", "wj")
+
+
+def test_a_silent_rank_is_an_error_on_every_rank_not_a_hang():
+    """Fault injection (MADGPU_P2P_TEST_DROP_SIGNAL): rank 2 stops signalling.  With the bounded wait its neighbours time out, the
+    flag travels with the next residual-norm all-reduce, and every rank returns the same error in the same cycle."""
+    env = dict(os.environ, FAKE_CUDA_WAIT_TIMEOUT_S="120", FAKE_NCCL_TIMEOUT_S="240")
+    r = subprocess.run([sys.executable, SCRIPT, "--world", "4", "--peer", "1", "--agglomerate-voxels", "1000", "--wait", "kernel", "--drop", "2:37"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "SLAB_EMULATION_TIMEOUT_REPORTED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "an arrival-counter wait timed out" in r.stdout
