@@ -1,7 +1,7 @@
 // ved_kernels.cuh -- the CUDA kernels of the VED tensor front-end (ved.cu) together with their launch geometry and the pass
 // structure of the separable Hessian.  Everything that decides WHAT is computed WHERE lives here, so that the CPU suite can run
-// this very source: tests/ved_host_harness.cpp includes this file after tests/cuda_host_shim.h, which maps the CUDA built-ins
-// (threadIdx, __shared__, __syncwarp, the <<<>>> launch behind VED_LAUNCH) onto host threads.  ved.cu adds only the context, the
+// this very source: tests/ved_host_harness.cpp includes this file after tests/mad_host/fiber_shim.h, which maps the CUDA
+// built-ins (threadIdx, __shared__, __syncwarp, the <<<>>> launch behind VED_LAUNCH) onto host fibres.  ved.cu adds only the context, the
 // C-ABI and the copies.  Arithmetic: ved_math.h.  Reference citations: ved.cu / ved_math.h.
 #ifndef MADGPU_VED_KERNELS_CUH
 #define MADGPU_VED_KERNELS_CUH

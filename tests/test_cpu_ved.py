@@ -6,7 +6,7 @@
 2. The source of the CUDA kernels themselves, compiled for the host by tests/ved_host_harness.cpp, against the oracle:
    csrc/ved_math.h (coefficient set-up, line recursion with fp32 intermediate storage, eigen-solver, vesselness, per-voxel update)
    and csrc/ved_kernels.cuh -- the unmodified __global__ kernels with their launch geometry and the pass structure of the
-   separable Hessian, run on host threads through tests/cuda_host_shim.h (threadIdx / __shared__ / __syncwarp / launch), so
+   separable Hessian, run on host fibres through tests/mad_host/fiber_shim.h (threadIdx / __shared__ / __syncwarp / launch), so
    indexing, the shared-memory tile walk of the x pass, ragged edges and buffer reuse are exercised as written.
    The tolerances found here are the ones tests/test_gpu_ved.py uses.
 No GPU, no compute call into libmadgpu.so; the context / C-ABI / copy layer of ved.cu is what only the GPU tests reach.
@@ -32,11 +32,11 @@ def host():
     """ved_math.h + ved_kernels.cuh compiled for the host."""
     csrc = os.path.join(ROOT, "multigridanisotropicdiffusion_b200", "csrc")
     src = os.path.join(ROOT, "tests", "ved_host_harness.cpp")
-    deps = [src, os.path.join(ROOT, "tests", "cuda_host_shim.h"), os.path.join(csrc, "ved_math.h"), os.path.join(csrc, "ved_kernels.cuh")]
+    deps = [src, os.path.join(ROOT, "tests", "mad_host", "fiber_shim.h"), os.path.join(ROOT, "tests", "fake_cuda", "cuda_runtime.h"), os.path.join(csrc, "ved_math.h"), os.path.join(csrc, "ved_kernels.cuh")]
     out = os.path.join(ROOT, "tests", "_build", "libvedhost.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-fno-gnu-unique", "-o", out, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas", "-fno-gnu-unique", "-I" + os.path.join(ROOT, "tests", "fake_cuda"), "-I" + os.path.join(ROOT, "tests"), "-o", out, src])
     L = C.CDLL(out)
     L.vh_rg_setup.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _dp]
     L.vh_rg_line.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, _fp, C.c_int, _fp, C.c_double]

@@ -1,7 +1,7 @@
 """The C-ABI layer of the VED front-end (multigridanisotropicdiffusion_b200/csrc/ved.cu: context, staging, chunking, call-sequence
 checks, statistics, the GenerateData loop of madved_run) driven on the CPU.
 
-tests/ved_cabi_host.cpp compiles ved.cu UNMODIFIED for the host: kernels on host threads (tests/cuda_host_shim.h), CUDA runtime
+tests/ved_cabi_host.cpp compiles ved.cu UNMODIFIED for the host: kernels on host fibres (tests/mad_host/fiber_shim.h), CUDA runtime
 calls on host memory (tests/fake_cuda/cuda_runtime.h), and the solver entry points madved_run calls answered by a stand-in backed by
 the oracle.  The resulting tests/_build/libmadved_host.so exports the same madved_* symbols as libmadgpu.so, and the product's own
 Python binding (multigridanisotropicdiffusion_b200.ved.MadVed) is pointed at it for the duration of a test, so these tests read like
@@ -24,7 +24,7 @@ VED_TEST = dict(alpha=0.5, beta=0.5, gamma=5.0, epsilon=0.01, omega=1.5, sensiti
 def hostlib():
     csrc = os.path.join(ROOT, "multigridanisotropicdiffusion_b200", "csrc")
     src = os.path.join(ROOT, "tests", "ved_cabi_host.cpp")
-    deps = [src, os.path.join(ROOT, "tests", "cuda_host_shim.h"), os.path.join(ROOT, "tests", "fake_cuda", "cuda_runtime.h"),
+    deps = [src, os.path.join(ROOT, "tests", "mad_host", "fiber_shim.h"), os.path.join(ROOT, "tests", "fake_cuda", "cuda_runtime.h"), os.path.join(ROOT, "tests", "fake_cuda", "cuda_runtime.h"),
             os.path.join(csrc, "ved.cu"), os.path.join(csrc, "ved_kernels.cuh"), os.path.join(csrc, "ved_math.h"),
             os.path.join(ROOT, "include", "madved.h"), os.path.join(ROOT, "include", "madgpu.h")]
     out = os.path.join(ROOT, "tests", "_build", "libmadved_host.so")

@@ -1,5 +1,5 @@
 // ved_cabi_host.cpp -- TEST INFRASTRUCTURE.  multigridanisotropicdiffusion_b200/csrc/ved.cu compiled UNMODIFIED for the host:
-// its kernels run on host threads (tests/cuda_host_shim.h), its CUDA runtime calls land in tests/fake_cuda/cuda_runtime.h, and the
+// its kernels run on host fibres (tests/mad_host/fiber_shim.h), its CUDA runtime calls land in tests/fake_cuda/cuda_runtime.h, and the
 // five madgpu_* entry points madved_run needs are answered by a stand-in solver backed by the CPU oracle (oracle/mad_oracle.c).
 // The result, tests/_build/libmadved_host.so, exports the same madved_* C-ABI as libmadgpu.so, so tests/test_cpu_ved_cabi.py can
 // drive the real context / staging / call-sequence code without a GPU.  Never part of the product.
@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "cuda_host_shim.h"
+#include "mad_host/fiber_shim.h"
 
 #include "../multigridanisotropicdiffusion_b200/csrc/ved.cu"
 

@@ -3,7 +3,7 @@
 //   csrc/ved_math.h       the arithmetic (coefficient set-up, line recursion with fp32 intermediate storage, eigen-solver,
 //                         vesselness, per-voxel update), plain host functions here;
 //   csrc/ved_kernels.cuh  the UNMODIFIED __global__ kernels, their launch geometry and the pass structure of the separable
-//                         Hessian, run on host threads through tests/cuda_host_shim.h (threadIdx, __shared__, __syncwarp, the
+//                         Hessian, run on host fibres through tests/mad_host/fiber_shim.h (threadIdx, __shared__, __syncwarp, the
 //                         launch behind VED_LAUNCH) -- indexing, tiling and buffer reuse are exercised exactly as written.
 // Built by tests/test_cpu_ved.py with g++ into tests/_build/.  The product never loads this file; the CUDA path never runs on
 // the CPU (ved.cu, the context / C-ABI / copies around these kernels, needs a device).
@@ -11,7 +11,7 @@
 #include <cstring>
 #include <vector>
 
-#include "cuda_host_shim.h"
+#include "mad_host/fiber_shim.h"
 
 #include "../multigridanisotropicdiffusion_b200/csrc/ved_kernels.cuh"
 
@@ -33,7 +33,7 @@ void vh_rg_line(double sigma, double spacing, int order, int normalize, const fl
   ved::rg_line<1>(x, 1, n, &c, out, &scale);
 }
 
-// hessian() of ved.cu: the kernels and launch geometry of ved_kernels.cuh executed by host threads.
+// hessian() of ved.cu: the kernels and launch geometry of ved_kernels.cuh executed by host fibres.
 // n = (nx, ny, nz); image nvox floats; H six planes of nvox floats.  Returns the number of kernel launches.
 int vh_hessian(const int* n, const double* h, double sigma, const float* image, float* H)
 {
