@@ -7,12 +7,15 @@
 #define FAKE_CUDA_RUNTIME_H
 
 #include <sched.h>
+#include <sys/mman.h>
 
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 // ---- vector types and dim3 (what the kernels of csrc/ use of vector_types.h) ----
 struct float2 { float x, y; };
@@ -57,9 +60,35 @@ constexpr size_t GUARD = 4096;
 constexpr unsigned char GUARD_BYTE = 0xA5;
 struct Header { size_t bytes; size_t magic; };
 }  // namespace fake_cuda
+namespace fake_cuda
+{
+// FAKE_CUDA_GUARD_PAGES=1 (2): every allocation ends (starts) at an inaccessible page, so that an out-of-bounds READ faults too
+// (electric-fence style; slow and memory-hungry, for one-off checks of the kernels' addressing)
+struct PageAlloc { char* base; size_t total; };
+inline std::mutex g_pages_m;
+inline std::map<void*, PageAlloc> g_pages;
+inline int guard_pages_mode()
+{
+  static const int m = std::getenv("FAKE_CUDA_GUARD_PAGES") ? std::atoi(std::getenv("FAKE_CUDA_GUARD_PAGES")) : 0;
+  return m;
+}
+}  // namespace fake_cuda
 inline cudaError_t cudaMalloc(void** p, size_t bytes)
 {
   using namespace fake_cuda;
+  if (guard_pages_mode()) {
+    const size_t pg = 4096, body = (bytes + 15) & ~(size_t)15, inner = (body + pg - 1) / pg * pg, total = inner + 2 * pg;
+    char* base = static_cast<char*>(mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (base == MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    mprotect(base, pg, PROT_NONE);
+    mprotect(base + total - pg, pg, PROT_NONE);
+    char* q = guard_pages_mode() == 2 ? base + pg : base + total - pg - body;
+    std::memset(q, 0xFF, body);
+    { std::lock_guard<std::mutex> g(g_pages_m); g_pages[q] = PageAlloc{base, total}; }
+    *p = q;
+    __atomic_add_fetch(&g_live_allocs, 1, __ATOMIC_RELAXED);
+    return cudaSuccess;
+  }
   char* raw = static_cast<char*>(std::malloc(bytes + 2 * GUARD));
   if (!raw) { *p = nullptr; return cudaErrorMemoryAllocation; }
   std::memset(raw, GUARD_BYTE, GUARD);
@@ -75,6 +104,19 @@ inline cudaError_t cudaFree(void* p)
 {
   using namespace fake_cuda;
   if (!p) return cudaSuccess;
+  if (guard_pages_mode()) {
+    PageAlloc a;
+    {
+      std::lock_guard<std::mutex> g(g_pages_m);
+      auto it = g_pages.find(p);
+      if (it == g_pages.end()) { std::fprintf(stderr, "fake_cuda: cudaFree of an unknown pointer %p\n", p); std::abort(); }
+      a = it->second;
+      g_pages.erase(it);
+    }
+    munmap(a.base, a.total);
+    __atomic_sub_fetch(&g_live_allocs, 1, __ATOMIC_RELAXED);
+    return cudaSuccess;
+  }
   char* raw = static_cast<char*>(p) - GUARD;
   Header h;
   std::memcpy(&h, raw, sizeof h);
