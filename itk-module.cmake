@@ -1,17 +1,15 @@
-set(DOCUMENTATION "B200 (sm_100a) drop-in for the multigrid anisotropic-diffusion module: the filters keep their names and
-template signatures, GenerateData() runs in libmadgpu (CUDA) through the C-ABI of include/madgpu.h / include/madved.h.")
+# ITK remote-module declaration of the B200 drop-in (read by ITK's module system when this directory is placed under
+# Modules/Remote or Modules/External; the standalone build in CMakeLists.txt does not use it).
+#
+# Dependencies: what the drop-in headers touch of ITK -- images, regions, iterators, ImageToImageFilter, image I/O for the tests.
+# ITKImageFeature, which the reference needs for itk::HessianRecursiveGaussianImageFilter, is NOT a dependency here: the Hessian of
+# the VED filter is computed by libmadgpu's own recursive-Gaussian kernels (include/madved.h).
+set(MADGPU_MODULE_DESCRIPTION
+    "Multigrid anisotropic diffusion and vessel enhancing diffusion on NVIDIA B200 (sm_100a): the filters keep their names and template signatures, GenerateData() runs in libmadgpu through the C-ABI of include/madgpu.h and include/madved.h.")
 
-# Same dependencies as the reference's itk-module.cmake minus ITKImageFeature: the Hessian of the VED filter is computed by
-# libmadgpu's own recursive-Gaussian kernels instead of itk::HessianRecursiveGaussianImageFilter.
 itk_module(MultigridAnisotropicDiffusion
-  DEPENDS
-    ITKCommon
-    ITKIOImageBase
-    ITKImageFilterBase
-    ITKImageGrid
-  TEST_DEPENDS
-    ITKTestKernel
-  EXCLUDE_FROM_DEFAULT
-  DESCRIPTION
-    "${DOCUMENTATION}"
-)
+  ENABLE_SHARED
+  DEPENDS ITKCommon ITKImageFilterBase ITKImageGrid ITKIOImageBase
+  TEST_DEPENDS ITKTestKernel
+  DESCRIPTION "${MADGPU_MODULE_DESCRIPTION}"
+  EXCLUDE_FROM_DEFAULT)
