@@ -168,8 +168,14 @@ def cpu_impl_kind(requested="auto"):
     """'reference' (oracle/_ref: the compiled reference headers) when that library is present, else 'port' (the C restatement)."""
     if requested in ("reference", "port"):
         return requested
-    from oracle import ref as R
-    return "reference" if R.available() else "port"
+    try:
+        from oracle import ref as R
+        if R.available():
+            R.lib()  # loadable here? (built in the authoring container, travels as an artefact)
+            return "reference"
+    except Exception:  # noqa: BLE001
+        pass
+    return "port"
 
 
 def _cpu_worker(a):
