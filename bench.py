@@ -457,10 +457,13 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        kind = cpu_impl_kind(args.cpu_impl)
-        size = args.cpu_size or (96 if kind == "reference" else 128)
-        r = cpu_reference_all_cores(size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0, host_procs(), kind)
-        cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": kind, "sample": cpu_sample_text(r, size, nu, args.cpu_steps)}
+        try:
+            kind = cpu_impl_kind(args.cpu_impl)
+            size = args.cpu_size or (96 if kind == "reference" else 128)
+            r = cpu_reference_all_cores(size, nu, 0 if args.smoother == "gs" else 1, args.cpu_steps, 0, host_procs(), kind)
+            cpu = {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": kind, "sample": cpu_sample_text(r, size, nu, args.cpu_steps)}
+        except Exception as e:  # noqa: BLE001 -- the GPU numbers above must still be printed
+            cpu = {"value": None, "unit": "Mvoxel/s", "cores": 0, "kind": "port", "sample": f"CPU baseline failed: {type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
