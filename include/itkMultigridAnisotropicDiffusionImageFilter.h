@@ -64,6 +64,7 @@ public:
   typedef typename TOutputImage::PixelType OutputPixelType;
   typedef double InternalPixelType;
   typedef Image<SymmetricSecondRankTensor<InputPixelType, TInputImage::ImageDimension>, TInputImage::ImageDimension> InputTensorImageType;
+  typedef typename InputTensorImageType::PixelType TensorPixelType;
   typedef InternalPixelType Precision;
 
   enum CycleType { VCYCLE, FMG, SMOOTHER };  // == MADGPU_CYCLE_V / _FMG / _SMOOTHER
@@ -79,8 +80,19 @@ public:
   itkSetMacro(Tolerance, Precision);
   itkSetMacro(Verbose, bool);
 
-  /** The tensor buffer is read during Update(); it must stay alive until then (the reference copies it here). */
-  void SetDiffusionTensor(const InputTensorImageType* inputTensor) { m_DiffusionTensor = inputTensor; }
+  /** Deep copy at Set time, as the reference does (.hxx:66-101): the caller may release, reuse or modify its tensor image
+   *  between this call and Update().  Only the pixel buffer is kept; the tensor image's spacing is ignored (.hxx:131). */
+  void SetDiffusionTensor(const InputTensorImageType* inputTensor)
+  {
+    m_TensorPixels = 0;
+    m_TensorCopy.clear();
+    if (inputTensor) {
+      m_TensorPixels = static_cast<size_t>(inputTensor->GetLargestPossibleRegion().GetNumberOfPixels());
+      const TensorPixelType* b = inputTensor->GetBufferPointer();
+      m_TensorCopy.assign(b, b + m_TensorPixels);
+    }
+    this->Modified();
+  }
 
   /** CUDA device ordinal (new; default 0). */
   itkSetMacro(Device, int);
@@ -91,7 +103,7 @@ public:
 protected:
   MultigridAnisotropicDiffusionImageFilter()
     : m_TimeStep(0.01), m_NumberOfSteps(1), m_Cycle(VCYCLE), m_IterationsPerGrid(2), m_Tolerance(1e-6), m_MaxCycles(100), m_Verbose(false),
-      m_Device(0), m_DiffusionTensor(nullptr)
+      m_Device(0), m_TensorPixels(0)
   {
     m_Stats = madgpu_stats();
   }
@@ -102,8 +114,10 @@ protected:
     const unsigned int Dim = TInputImage::ImageDimension;
     const InputImageType* input = this->GetInput();
     if (!input) itkExceptionMacro(<< "no input image");
-    if (!m_DiffusionTensor) itkExceptionMacro(<< "no diffusion tensor (SetDiffusionTensor)");
+    if (m_TensorCopy.empty()) itkExceptionMacro(<< "no diffusion tensor (SetDiffusionTensor)");
     const typename InputImageType::RegionType region = input->GetLargestPossibleRegion();
+    if (m_TensorPixels != static_cast<size_t>(region.GetNumberOfPixels()))
+      itkExceptionMacro(<< "the diffusion tensor image has " << m_TensorPixels << " pixels, the input image " << region.GetNumberOfPixels());
 
     madgpu_params p;
     madgpu_params_default(&p);
@@ -129,7 +143,7 @@ protected:
       ~Guard() { madgpu_destroy(c); }
     } guard = {ctx};
 
-    if (this->SetTensor(ctx, m_DiffusionTensor->GetBufferPointer(), region.GetNumberOfPixels()) != MADGPU_OK)
+    if (this->SetTensor(ctx, m_TensorCopy.data(), m_TensorPixels) != MADGPU_OK)
       itkExceptionMacro(<< "madgpu_set_tensor: " << madgpu_last_error(ctx));
 
     typename OutputImageType::Pointer outputImage = OutputImageType::New();
@@ -176,7 +190,8 @@ private:
   unsigned int m_MaxCycles;
   bool m_Verbose;
   int m_Device;
-  const InputTensorImageType* m_DiffusionTensor;
+  std::vector<TensorPixelType> m_TensorCopy;  // SetDiffusionTensor's deep copy (the reference keeps an InternalTensorImage)
+  size_t m_TensorPixels;
   madgpu_stats m_Stats;
 
   MultigridAnisotropicDiffusionImageFilter(const Self&);

@@ -36,6 +36,7 @@ extern "C" {
 #define MADGPU_ENOMEM (-3)   /* device or host allocation failed                     */
 #define MADGPU_ESTATE (-4)   /* call sequence error (e.g. solve before set_tensor)  */
 #define MADGPU_ESINGULAR (-5)/* coarsest-grid operator is singular                   */
+#define MADGPU_ENUMERIC (-6) /* the relative residual became non-finite (diverged / overflowed); no image returned */
 
 /* TSmootherType template argument of the reference filter
  * (itkMultigridAnisotropicDiffusionImageFilter.h:89-92) as a run-time tag. */

@@ -16,7 +16,7 @@ MADGPU_MAX_STEPS = 64
 SMOOTHER_GS, SMOOTHER_WJ = 0, 1
 CYCLE_V, CYCLE_FMG, CYCLE_SMOOTHER = 0, 1, 2
 PIX_U8, PIX_I16, PIX_F32, PIX_F64 = 0, 1, 2, 3
-OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESINGULAR = 0, -1, -2, -3, -4, -5
+OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESINGULAR, ENUMERIC = 0, -1, -2, -3, -4, -5, -6
 
 K_NAMES = ["smooth0", "smoothc", "resid0", "restrict", "prolong", "coarse", "misc", "halo"]
 

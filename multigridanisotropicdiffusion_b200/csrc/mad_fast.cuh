@@ -463,6 +463,11 @@ enum { MODE_WJ = 0, MODE_RES = 1, MODE_COEF = 2, MODE_RES_C32 = 3 };
 // five 16-byte words; word i holds entries 2i and 2i+1, each for the four voxels.  Entries: 0 1/diag, then the
 // off-diagonal coefficients DIVIDED by diag: 1 x+, 2 x-, 3 y+, 4 y-, 5 z+, 6 z-, 7 xy edges, 8 xz edges, 9 yz edges.
 constexpr int COEF_WORDS = 5;
+// Entry 0 is stored as (1/diag) * 2^14: diag = 1 + 2 dt sum_d D_dd / h_d^2 >= 1 grows with dt / h^2 (small spacings, large time
+// steps), and a plain fp16 1/diag would lose bits below 6.1e-5 (diag > 1.6e4) and flush to zero beyond 3.4e7.  Scaled by a power
+// of two (exact) the entry stays a normal fp16 number for diag < 2^28; the packing kernel reports rows beyond COEF_DIAG_MAX so that
+// the host keeps the exact-row sweep for such a level instead of relaxing with a denormal diagonal.
+constexpr float COEF_INV_SCALE = 16384.f, COEF_INV_UNSCALE = 1.f / 16384.f, COEF_DIAG_MAX = 1.0e8f;
 __device__ __forceinline__ size_t coef_quad(const Geom& g, int x4, int y, int z) { return ((size_t)z * g.ny + y) * (size_t)(g.pitch >> 2) + x4; }
 
 // One pass over the volume.  MODE_WJ: out = weighted-Jacobi update of u.  MODE_RES: out = f - A u
@@ -540,7 +545,8 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
           const float i0 = 1.f / float(c.diag[j]), i1 = 1.f / float(c.diag[j + 1]);
-          h[0][j >> 1] = __floats2half2_rn(i0, i1);
+          h[0][j >> 1] = __floats2half2_rn(i0 * COEF_INV_SCALE, i1 * COEF_INV_SCALE);
+          if (partials && (!(float(c.diag[j]) < COEF_DIAG_MAX) || !(float(c.diag[j + 1]) < COEF_DIAG_MAX))) partials[0] = 1.0;  // benign race: every writer stores 1
           h[1][j >> 1] = __floats2half2_rn(float(c.xp[j]) * i0, float(c.xp[j + 1]) * i1);
           h[2][j >> 1] = __floats2half2_rn(float(c.xm[j]) * i0, float(c.xm[j + 1]) * i1);
           h[3][j >> 1] = __floats2half2_rn(float(c.yp[j]) * i0, float(c.yp[j + 1]) * i1);
@@ -747,6 +753,8 @@ __device__ __forceinline__ float coef_at(const CoefRaw& r, int k, int j)
   const __half2 h = *reinterpret_cast<const __half2*>(&u);
   return (j & 1) ? __high2float(h) : __low2float(h);
 }
+// 1/diag of voxel j (entry 0 without its storage scale)
+__device__ __forceinline__ float coef_inv(const CoefRaw& r, int j) { return coef_at(r, 0, j) * COEF_INV_UNSCALE; }
 // normalised off-diagonal sum at slot j
 __device__ __forceinline__ float offdiag16(const CoefRaw& c, const UPlane<float>& m, const UPlane<float>& q, const UPlane<float>& n, int j)
 {
@@ -829,16 +837,16 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_gs(Geom g, const uint4* 
           }
           if (p.xb) { mirror_x(uc.r[0], p.xt, p.jl); mirror_x(uc.r[2], p.xt, p.jl); }
         }
-        const float n0 = fv.v[0] * coef_at(c, 0, 0) - offdiag16(c, um, uc, up, 0);
-        const float n2 = fv.v[2] * coef_at(c, 0, 2) - offdiag16(c, um, uc, up, 2);
+        const float n0 = fv.v[0] * coef_inv(c, 0) - offdiag16(c, um, uc, up, 0);
+        const float n2 = fv.v[2] * coef_inv(c, 2) - offdiag16(c, um, uc, up, 2);
         uc.r[1].v[1] = n0; uc.r[1].v[3] = n2;
         {
           const float r = __shfl_down_sync(FULL, n0, 1);
           if (p.lane < 31) uc.r[1].v[5] = r;
           if (p.xb) mirror_x(uc.r[1], p.xt, p.jl);
         }
-        const float n1 = fv.v[1] * coef_at(c, 0, 1) - offdiag16(c, um, uc, up, 1);
-        const float n3 = fv.v[3] * coef_at(c, 0, 3) - offdiag16(c, um, uc, up, 3);
+        const float n1 = fv.v[1] * coef_inv(c, 1) - offdiag16(c, um, uc, up, 1);
+        const float n3 = fv.v[3] * coef_inv(c, 3) - offdiag16(c, um, uc, up, 3);
         uc.r[1].v[2] = n1; uc.r[1].v[4] = n3;
         {
           const float l = __shfl_up_sync(FULL, n3, 1);
@@ -935,16 +943,16 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
     if (z == g.nz - 1 && g.zhi_phys) up = um;  // mirrored plane z+1 == plane z-1, already relaxed
     // relax one of the warp's two rows: even x, then odd x (x-neighbours through shuffles)
     auto relax = [&](int row, const CoefRaw& c, const V4<float>& fv, int orow) {
-      const float n0 = fv.v[0] * coef_at(c, 0, 0) - offdiag16_rows(c, um, uc, up, row, 0);
-      const float n2 = fv.v[2] * coef_at(c, 0, 2) - offdiag16_rows(c, um, uc, up, row, 2);
+      const float n0 = fv.v[0] * coef_inv(c, 0) - offdiag16_rows(c, um, uc, up, row, 0);
+      const float n2 = fv.v[2] * coef_inv(c, 2) - offdiag16_rows(c, um, uc, up, row, 2);
       uc.r[row].v[1] = n0; uc.r[row].v[3] = n2;
       {
         const float r = __shfl_down_sync(FULL, n0, 1);
         if (lane < 31) uc.r[row].v[5] = r;
         if (p.xb) mirror_x(uc.r[row], p.xt, p.jl);
       }
-      const float n1 = fv.v[1] * coef_at(c, 0, 1) - offdiag16_rows(c, um, uc, up, row, 1);
-      const float n3 = fv.v[3] * coef_at(c, 0, 3) - offdiag16_rows(c, um, uc, up, row, 3);
+      const float n1 = fv.v[1] * coef_inv(c, 1) - offdiag16_rows(c, um, uc, up, row, 1);
+      const float n3 = fv.v[3] * coef_inv(c, 3) - offdiag16_rows(c, um, uc, up, row, 3);
       uc.r[row].v[2] = n1; uc.r[row].v[4] = n3;
       {
         const float l = __shfl_up_sync(FULL, n3, 1);
@@ -1006,7 +1014,7 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_coef_residual(Geom g, const u
     float res[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float inv = coef_at(c, 0, j);
+      const float inv = coef_inv(c, j);
       // rows are stored divided by diag: A u = (u + sum_k c_k u_k) / inv
       res[j] = __fdividef(fv.v[j] * inv - uc.r[1].v[j + 1] - offdiag16(c, um, uc, up, j), inv);
     }

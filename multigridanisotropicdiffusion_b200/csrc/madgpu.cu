@@ -54,6 +54,7 @@ struct Level {
   float* D[6];
   uint4* coef16;      // packed fp16 operator rows for the Gauss-Seidel smoother (mad_fast.cuh), built on first use
   bool coef16_valid;
+  bool coef16_off;    // some diagonal of this level is beyond the range of the packed rows (fast::COEF_DIAG_MAX): exact-row sweeps instead
   std::vector<void*> allocs;
 };
 
@@ -496,6 +497,39 @@ void op_zero(madgpu_ctx* ctx, Level& L, float* p)
   cudaMemsetAsync(p, 0, (size_t)L.g.plane * L.g.nz * sizeof(float), ctx->stream);
 }
 
+double read_scalar(madgpu_ctx* ctx);
+
+// Packed fp16 operator rows of a level (fast::MODE_COEF), built once per tensor.  False when the level cannot use them: out of
+// device memory (latched as an error) or a diagonal beyond the range of the packed 1/diag (the level then keeps exact rows).
+bool build_coef16(madgpu_ctx* ctx, Level& L)
+{
+  if (L.coef16_valid) return true;
+  if (!L.coef16) {
+    void* q = nullptr;
+    const size_t bytes = (size_t)L.g.nz * L.g.ny * (size_t)(L.g.pitch >> 2) * fast::COEF_WORDS * sizeof(uint4);
+    if (cudaMalloc(&q, bytes) != cudaSuccess) {
+      if (ctx->sticky.empty()) ctx->sticky = "out of device memory for the packed Gauss-Seidel rows";
+      cudaGetLastError();
+      L.coef16_off = true;
+      return false;
+    }
+    L.allocs.push_back(q);
+    L.coef16 = (uint4*)q;
+  }
+  {
+    Scope sb(ctx, MADGPU_K_MISC);
+    cudaMemsetAsync(ctx->d_scalar + 2, 0, sizeof(double), ctx->stream);
+    launch_fast<fast::MODE_COEF, float, float, float, float>(ctx, L, L.u, L.f, reinterpret_cast<float*>(L.coef16), ctx->d_scalar + 2, 0.f);
+  }
+  double flag = 0.0;  // once per tensor and level: a host round trip is affordable here
+  cudaMemcpyAsync(ctx->h_scalar + 2, ctx->d_scalar + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  flag = ctx->h_scalar[2];
+  if (flag != 0.0) { L.coef16_off = true; return false; }
+  L.coef16_valid = true;
+  return true;
+}
+
 // n_iter smoother iterations on (L.u, L.f); result in L.u (pointers may be swapped with L.tmp).
 // zero_first: the iterate is identically zero on entry (every V-cycle leg starts like that): the streaming kernels then
 // skip reading it (and the memset that would have produced it); the generic kernels get the memset.
@@ -519,20 +553,8 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       else MAD_LAUNCH((k_jacobi<2>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       if (!use_fast(ctx, L)) halo_dirty(ctx, L.tmp);
       std::swap(L.u, L.tmp);
-    } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16) {
+    } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && build_coef16(ctx, L)) {
       // fused sweep fed by pre-evaluated fp16 operator rows (built once per tensor and level)
-      if (!L.coef16_valid) {
-        if (!L.coef16) {
-          void* q = nullptr;
-          const size_t bytes = (size_t)L.g.nz * L.g.ny * (size_t)(L.g.pitch >> 2) * fast::COEF_WORDS * sizeof(uint4);
-          if (cudaMalloc(&q, bytes) != cudaSuccess) { latch(ctx, 0, ""); ctx->sticky = "out of device memory for the packed Gauss-Seidel rows"; cudaGetLastError(); return; }
-          L.allocs.push_back(q);
-          L.coef16 = (uint4*)q;
-        }
-        Scope sb(ctx, MADGPU_K_MISC);
-        launch_fast<fast::MODE_COEF, float, float, float, float>(ctx, L, L.u, L.f, reinterpret_cast<float*>(L.coef16), nullptr, 0.f);
-        L.coef16_valid = true;
-      }
       Scope s(ctx, cls);
       if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
         const int zc = fast_zc(L.g, 8);
@@ -615,7 +637,7 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
   Scope s(ctx, MADGPU_K_RESTRICT, norm ? 2 : 1);
   const Tensor D = tensor_of(L);
   double* part = norm ? ctx->partials : nullptr;
-  if (!norm && ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && L.coef16_valid) {
+  if (!norm && ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && L.coef16_valid) {
     // inside a Gauss-Seidel V-cycle: residual with the packed rows the sweeps use
     const int zc = fast_zc(L.g, 4);
     Geom gg = L.g;
@@ -1055,7 +1077,7 @@ int build_coarse_solver(madgpu_ctx* ctx)
 // After level-0 tensor planes are filled: restrict them down the hierarchy and build the coarse solver.
 int finish_tensor(madgpu_ctx* ctx)
 {
-  for (int l = 0; l < ctx->nlevels; ++l) ctx->lv[l].coef16_valid = false;
+  for (int l = 0; l < ctx->nlevels; ++l) { ctx->lv[l].coef16_valid = false; ctx->lv[l].coef16_off = false; }
   for (int l = 0; l + 1 < ctx->nlevels; ++l)
     for (int c = 0; c < ctx->ncomp; ++c)  // mad/itkGridsHierarchy.hxx:149-162
       op_restrict<float>(ctx, l, ctx->lv[l].D[c], ctx->lv[l + 1].D[c], MADGPU_K_MISC);
@@ -1196,6 +1218,9 @@ int run_steps(madgpu_ctx* ctx)
       outer_iteration(ctx, P.cycle == MADGPU_CYCLE_SMOOTHER);
       relres = std::sqrt(read_scalar(ctx)) / rhs_norm;
       if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());  // e.g. a halo wait timed out: every rank sees it in the same cycle
+      // a NaN would end the do-while below ("relres > tolerance" is false) and hand back a NaN image with rc 0.  (A zero image
+      // keeps the reference's behaviour: 0/0 at …Filter.hxx:204,217 ends its loop after one cycle and the zero image comes back.)
+      if (!std::isfinite(relres) && rhs_norm > 0.0) return fail(ctx, MADGPU_ENUMERIC, "time step %d, cycle %d: the relative residual is not finite (%g) -- diverged or overflowed", n, it + 1, relres);
       ctx->relres_hist[(size_t)n * P.max_cycles + it] = relres;
       if (P.verbose && ctx->rank == 0) {
         if (P.cycle == MADGPU_CYCLE_SMOOTHER) printf("Smoother iteration n. %d: relative residual = %g\n", it + 1, relres);
@@ -1433,6 +1458,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     }
     L.coef16 = nullptr;
     L.coef16_valid = false;
+    L.coef16_off = false;
     for (int c = 0; c < 6; ++c) L.D[c] = nullptr;
     for (int c = 0; c < ctx->ncomp; ++c) {
       int rc = dalloc(ctx, L.allocs, &L.D[c], L.elems);
@@ -1659,6 +1685,7 @@ int madgpu_cycles_run(madgpu_ctx* ctx, int32_t n, double* relres, float* device_
     const double r = std::sqrt(read_scalar(ctx)) / ctx->rhs_norm;
     if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
     if (relres) relres[i] = r;
+    if (!std::isfinite(r) && ctx->rhs_norm > 0.0) return fail(ctx, MADGPU_ENUMERIC, "cycle %d: the relative residual is not finite (%g)", i + 1, r);
   }
   CU(cudaEventRecord(ctx->ev_b, ctx->stream));
   CU(cudaEventSynchronize(ctx->ev_b));
@@ -1736,7 +1763,7 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (!ctx || !tile || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
   const Level& L = ctx->lv[level];
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
-    const int wy = ctx->gs_coef16 ? (gs_pairs(ctx, L) ? 8 : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
+    const int wy = (ctx->gs_coef16 && !L.coef16_off) ? (gs_pairs(ctx, L) ? 8 : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
     tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level

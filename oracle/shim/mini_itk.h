@@ -125,8 +125,11 @@ public:
   void Register() const { ++m_RefCount; }
   void UnRegister() const { if (--m_RefCount <= 0) delete this; }
   virtual const char* GetNameOfClass() const { return "LightObject"; }
+  virtual void Modified() const { ++m_MTime; }  // itk::Object's modification stamp (what itkSetMacro bumps in real ITK)
+  unsigned long GetMTime() const { return m_MTime; }
 private:
   mutable long m_RefCount;
+  mutable unsigned long m_MTime = 0;
 };
 
 template <typename T>

@@ -59,6 +59,10 @@ static int run(char** a, const int* n, const double* h)
   typename FilterType::Pointer filter = FilterType::New();
   filter->SetInput(img);
   filter->SetDiffusionTensor(tensor);
+  // the reference deep-copies the tensor at Set time (.hxx:66-101): scribbling over the caller's image and dropping the last
+  // reference before Update() is valid usage and must not change the result
+  tensor->FillBuffer(typename TensorImageType::PixelType());
+  tensor = nullptr;
   filter->SetIterationsPerGrid(static_cast<unsigned int>(std::atoi(a[4])));
   filter->SetTimeStep(std::atof(a[5]));
   filter->SetTolerance(std::atof(a[6]));

@@ -72,6 +72,44 @@ def test_streaming_kernels_solve_matches_oracle(MadSolver, host, monkeypatch, sm
     assert rel_l2(out, ref) < (1e-5 if smoother == "wj" else 1e-4)
 
 
+def test_packed_rows_with_a_large_diagonal(MadSolver, monkeypatch):
+    """Small spacings (SI units) make diag = 1 + 2 dt sum D_dd / h^2 large.  The packed Gauss-Seidel rows keep 1/diag scaled by
+    2^14 (a plain fp16 1/diag is subnormal beyond 1.6e4 and zero beyond 3.4e7 -> a NaN image with rc 0).  h = 2e-3: diag ~ 1e4..4e5."""
+    monkeypatch.setenv("MADGPU_FAST_MIN_NX", "8")
+    h = 2e-3
+    shape, sp = (12, 16, 64), (h, h, 1.6 * h)
+    T, img = random_spd_tensor(shape, seed=3), random_image(shape, seed=6)
+    with MadSolver(shape, sp, time_step=0.1, smoother=0, iterations_per_grid=3, tolerance=1e-8, max_cycles=60) as s:
+        s.set_tensor(T)
+        out = s.solve(img, out_dtype=np.float64)
+        st = s.last_stats
+        assert s.gs_tile(0)[1] == 8  # the row-pair packed sweep (128 x 8 tiles)
+    o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=0, nu=3)
+    ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-8, max_cycles=60)
+    assert np.isfinite(out).all() and st["final_relres"][0] <= 1e-8
+    assert st["cycles_per_step"][0] <= cyc[0] + 2  # a stiff system (dt / h^2 = 2.5e4): ~20 cycles either way
+    assert rel_l2(out, ref) < 1e-4
+
+
+def test_diagonal_beyond_the_packed_range_falls_back_or_fails_loudly(MadSolver, monkeypatch):
+    """dt / h^2 = 2.5e8: diag > 1e8 leaves the range of the packed rows -> the level is relaxed with exact rows (128 x 4 tiles).
+    fp32 cycles cannot solve a system this stiff (the fp64 reference can); what is checked is that the call never hands back
+    NaNs with rc 0: either finite numbers or MADGPU_ENUMERIC."""
+    from multigridanisotropicdiffusion_b200 import MadGpuError
+    monkeypatch.setenv("MADGPU_FAST_MIN_NX", "8")
+    h = 2e-5
+    shape, sp = (12, 16, 64), (h, h, 1.6 * h)
+    T, img = random_spd_tensor(shape, seed=3), random_image(shape, seed=6)
+    with MadSolver(shape, sp, time_step=0.1, smoother=0, iterations_per_grid=3, tolerance=1e-8, max_cycles=5) as s:
+        s.set_tensor(T)
+        try:
+            out = s.solve(img, out_dtype=np.float64)
+            assert np.isfinite(out).all()
+        except MadGpuError as e:
+            assert "not finite" in str(e)
+        assert s.gs_tile(0)[1] == 4
+
+
 def test_operators_and_casts(MadSolver):
     """Per-operator entry points on a mixed-centring hierarchy, FMG, smoother-only mode, integer pixels."""
     shape, sp = (14, 25, 12), (0.33, 0.33, 0.33)
