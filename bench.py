@@ -238,7 +238,9 @@ def run_reference_arm(args):
         "metric": "3D VED V-cycle Mvoxels/s at 512^3", "value": r["mvox_s"], "unit": "Mvoxel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_cycle"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, "replicas" if args.gpus > 1 else "single"),
+        "config": dict(workload_config(args, f"host CPU: {r['procs']} independent single-threaded solves"), size=[size] * 3, full_size=[args.size] * 3,
+                       sample=f"bounded sample of the {args.size}^3 workload: {r['procs']} concurrent {size}^3 volumes of the same phantom and tensor "
+                              f"(the reference's ~1 KB/voxel StencilImage cannot hold {args.size}^3)"),
         "cpu_baseline": {"value": r["mvox_s"], "unit": "Mvoxel/s", "cores": r["procs"], "kind": kind,
                          "sample": cpu_sample_text(r, size, nu, args.steps + (args.warmup if kind == "reference" else 0))},
         "e2e": {"value": r["mvox_s"], "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -281,6 +283,121 @@ def run_ved_filter(args, img_np, device):
             "_launches": int(vst["kernel_launches"])}
 
 
+def timed_cycles(s, steps, warmup, barrier, gpu_index):
+    """W untimed cycles, then exactly K cycles bracketed by barrier + synchronize; clocks sampled through both (same kernels)."""
+    sampler = ClockSampler(gpu_index)
+    sampler.start()
+    time.sleep(0.3)  # nvidia-smi needs ~0.2 s to start
+    if warmup > 0:
+        s.cycles_run(warmup)
+    s.set_profiling(True)
+    barrier()
+    t_wall = time.perf_counter()
+    relres, dev_ms, st = s.cycles_run(steps)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop()
+    s.set_profiling(False)
+    return relres, dev_ms, st, clocks, wall_ms
+
+
+def make_slab_solver(shape_global, smoother, nu, local_rank, rank, world, want_peer, **kw):
+    """One z-slab context per rank (madgpu_create_slab) + the peer-memory halo when asked for and granted on every rank."""
+    from multigridanisotropicdiffusion_b200 import MadSolver, phantom, slabs
+    s = MadSolver(shape_global, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, device=local_rank,
+                  rank=rank, world_size=world, nccl_id=slabs.create_unique_id(), **kw)
+    peer = bool(want_peer) and slabs.enable_peer_halo(s)
+    return s, peer
+
+
+def slab_parity(rank, world, local_rank, dev, want_peer):
+    """Hardware evidence for the z-slab path inside the driver's own N > 1 run (the multi-GPU pytest files skip on a 1-GPU box): a
+    128 x 128 x 32N volume is solved as N slabs, gathered on rank 0 and compared with the single-GPU solve of the whole volume
+    there -- weighted Jacobi and Gauss-Seidel, V-cycles and FMG (itkMultigridAnisotropicDiffusionImageFilter.hxx:207-246, 300-338).
+    Bounds: WJ is the same iteration (same cycle counts, rel-L2 <= 1e-6), GS relaxes slab faces like tile faces (<= 1e-4)."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from multigridanisotropicdiffusion_b200 import MadSolver, phantom, slabs
+    shape = (32 * world, 128, 128)
+    img_t, D = phantom.vessel_phantom(shape, device=dev)
+    img = img_t.cpu().numpy()
+    T = phantom.planes_to_aos(D).cpu().numpy()
+    del img_t, D
+    out = {"volume": [128, 128, 32 * world], "tolerance": 1e-9, "nu": 3}
+    kw = dict(tolerance=1e-9, max_cycles=40, number_of_steps=1)
+    s, peer = make_slab_solver(shape, MadSolver.GS, 3, local_rank, rank, world, want_peer, **kw)
+    out["halo"] = "peer stores" if peer else "nccl"
+    s.set_tensor(slabs.cut(T, rank, world))
+    r = None
+    if rank == 0:
+        r = MadSolver(shape, phantom.VED_SPACING, time_step=0.1, smoother=MadSolver.GS, iterations_per_grid=3, device=local_rank, **kw)
+        r.set_tensor(T)
+    ok = True
+    for name, sm, cyc, bound in (("wj_v", MadSolver.WJ, MadSolver.VCYCLE, 1e-6), ("gs_v", MadSolver.GS, MadSolver.VCYCLE, 1e-4),
+                                 ("wj_fmg", MadSolver.WJ, MadSolver.FMG, 1e-6), ("gs_fmg", MadSolver.GS, MadSolver.FMG, 1e-4)):
+        s.set_solver(smoother=sm, cycle=cyc)
+        local = s.solve(slabs.cut(img, rank, world), out_dtype=np.float64)
+        cs = s.last_stats["cycles_per_step"][0]
+        full = slabs.gather_volume(local)
+        if rank == 0:
+            r.set_solver(smoother=sm, cycle=cyc)
+            ref = r.solve(img, out_dtype=np.float64)
+            cr = r.last_stats["cycles_per_step"][0]
+            err = float(np.linalg.norm(full - ref) / np.linalg.norm(ref))
+            good = err <= bound and (cs == cr if sm == MadSolver.WJ else abs(cs - cr) <= 2) and s.last_stats["final_relres"][0] <= 1e-9
+            out[name] = {"rel_l2": err, "cycles_slab": cs, "cycles_single": cr, "cycles_equal": cs == cr, "bound": bound, "ok": bool(good)}
+            ok = ok and good
+        dist.barrier()
+    s.close()
+    if r is not None:
+        r.close()
+    out["ok"] = bool(ok)
+    return out
+
+
+def extra_volume_run(shape_global, args, smoother, rank, world, local_rank, dev, want_peer, barrier, active=True):
+    """K timed cycles on another volume with the same settings (own clock record): the 1024^3 z-slab run of BASELINE.json configs[4]
+    and the one-GPU 512^3 run it is compared with.  world == 1 -> plain single-GPU context on this rank."""
+    import numpy as np
+    import torch
+
+    from multigridanisotropicdiffusion_b200 import MadSolver, phantom, slabs
+    if not active:
+        return None
+    nz = shape_global[0]
+    if world > 1:
+        z0, z1 = slabs.slab_range(nz, rank, world)
+        img, D = phantom.vessel_phantom(shape_global, device=dev, z_range=(z0, z1))
+        s, peer = make_slab_solver(shape_global, smoother, args.nu, local_rank, rank, world, want_peer, tolerance=0.0, max_cycles=1 << 20)
+    else:
+        img, D = phantom.vessel_phantom(shape_global, device=dev)
+        s, peer = MadSolver(shape_global, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=args.nu, tolerance=0.0,
+                            max_cycles=1 << 20, device=local_rank), False
+    torch.cuda.synchronize()
+    s.set_tensor_device([D[c].data_ptr() for c in range(6)])
+    s.cycles_begin(d_in=img.data_ptr())
+    del D
+    relres, dev_ms, st, clocks, _ = timed_cycles(s, args.steps, max(args.warmup, 3), barrier, local_rank)
+    ms = dev_ms / args.steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nvox = int(np.prod(shape_global))
+    res = {"size": [shape_global[2], shape_global[1], shape_global[0]], "n_gpus": world, "value": nvox / (ms * 1e-3) / 1e6, "unit": "Mvoxel/s",
+           "ms_per_step": ms, "steps": args.steps, "halo": ("peer stores" if peer else "nccl") if world > 1 else None, "clocks": clocks,
+           "class_ms_per_cycle": {k: v / args.steps for k, v in st["prof_ms"].items() if v > 0},
+           "cycle_frac": alg_bytes_per_cycle(args.nu) * nvox / world / (ms * 1e-3) / 1e9 / measured_peaks()[0],
+           "relres_after_timed_cycles": float(relres[-1]) if len(relres) else None}
+    s.close()
+    del img
+    torch.cuda.empty_cache()
+    return res
+
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -309,28 +426,21 @@ def run_ours(args):
     smoother = MadSolver.GS if args.smoother == "gs" else MadSolver.WJ
     slab_mode = world > 1 and not args.replicas
     peer_halo = False
+    want_peer = False
     if slab_mode:
-        # ONE volume cut into z-slabs, one per GPU (strong scaling): NCCL halo exchange inside libmadgpu.so
+        # ONE volume cut into z-slabs, one per GPU (strong scaling); halo = peer stores from the producing kernels (CUDA IPC over
+        # NVLink) with bounded in-stream waits, NCCL send/recv where the library or a rank declines
         from multigridanisotropicdiffusion_b200 import slabs
         z0, z1 = slabs.slab_range(n, rank, world)
         img, D = phantom.vessel_phantom(shape, device=dev, z_range=(z0, z1))
         torch.cuda.synchronize()
-        # peer-memory halo (NVLink stores from the producing kernels): verified on 2 and 4 GPUs; an 8-rank run hung in this
-        # round and could not be diagnosed before the GPU budget ran out, so beyond 4 ranks NCCL send/recv stays the default
-        want_peer = args.peer_halo or (not args.nccl_halo and world <= 4)
+        want_peer = not args.nccl_halo and (world <= 4 or args.peer_halo or os.environ.get("MADGPU_BENCH_PEER8") == "1")
         if want_peer and world > 4:
             # beyond the rank counts verified on hardware: arrival counters awaited by the bounded k_halo_wait, so that a signal that
             # never arrives costs a time-out and an error on every rank (handled below) instead of a hung stream
             os.environ["MADGPU_P2P_WAIT"] = "kernel"
             os.environ.setdefault("MADGPU_P2P_TIMEOUT_MS", "3000")
-
-        def make_slab_solver():
-            return MadSolver(shape_global, phantom.VED_SPACING, time_step=0.1, smoother=smoother, iterations_per_grid=nu, tolerance=0.0,
-                             max_cycles=1 << 20, device=local_rank, rank=rank, world_size=world, nccl_id=slabs.create_unique_id())
-
-        shape_global = shape
-        s = make_slab_solver()
-        peer_halo = want_peer and slabs.enable_peer_halo(s)
+        s, peer_halo = make_slab_solver(shape, smoother, nu, local_rank, rank, world, want_peer, tolerance=0.0, max_cycles=1 << 20)
         if peer_halo and world > 4:
             # trial cycles: a time-out is reported by every rank in the same cycle (the flag travels with the norm all-reduce)
             try:
@@ -342,8 +452,8 @@ def run_ours(args):
                     print(f"bench.py: peer-memory halo failed on {world} ranks ({e}); falling back to the NCCL halo", file=sys.stderr, flush=True)
                 s.close()
                 os.environ["MADGPU_P2P_WAIT"] = "memop"
-                s = make_slab_solver()
-                peer_halo = False
+                want_peer = False
+                s, peer_halo = make_slab_solver(shape, smoother, nu, local_rank, rank, world, False, tolerance=0.0, max_cycles=1 << 20)
     else:
         img, D = phantom.vessel_phantom(shape, device=dev)
         torch.cuda.synchronize()
@@ -354,21 +464,7 @@ def run_ours(args):
     s.set_tensor_device([D[c].data_ptr() for c in range(6)])
     s.cycles_begin(d_in=img.data_ptr())
     # ---- device-resident timing: W warm-up cycles, then exactly K cycles ----
-    # clock sampler: nvidia-smi needs ~0.2 s to start, so it is launched before the warm-up and keeps sampling through
-    # the timed region (both run the same kernels back to back)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    if args.warmup > 0:
-        s.cycles_run(args.warmup)
-    s.set_profiling(True)
-    barrier()
-    t_wall = time.perf_counter()
-    relres, dev_ms, st = s.cycles_run(args.steps)
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall) * 1e3
-    clocks = sampler.stop()
-    s.set_profiling(False)
+    relres, dev_ms, st, clocks, wall_ms = timed_cycles(s, args.steps, args.warmup, barrier, local_rank)
     ms_per_step = dev_ms / args.steps
     if world > 1:
         t = torch.tensor([ms_per_step], device=dev, dtype=torch.float64)
@@ -384,22 +480,28 @@ def run_ours(args):
     sm_launches = st["prof_launches"]["smooth0"]
     sweeps = 2 * nu * args.steps
     achieved = ALG_BYTES_SWEEP_3D * nvox * sweeps / (sm_ms * 1e-3) / 1e9 if sm_ms > 0 else None
-    traffic = None
+    tile = s.gs_tile(0) if args.smoother == "gs" else None
+    launched_kernel = ("k_fast_sweep<MODE_WJ>" if args.smoother == "wj" else
+                       "k_coef_gs2" if tile and tile[1] == 8 else "k_coef_gs" if tile else "k_gs_color")
+    traffic, traffic_src = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
         for key in ("smooth0", "smooth0_" + args.smoother):
             ent = prof.get(key, {})
-            if ent.get("size") == n and ent.get("smoother") == args.smoother and world == 1:
-                traffic = ent.get("dram_bytes_per_launch")
+            # only a capture of the kernel that was actually launched, at this size, counts
+            if ent.get("size") == n and ent.get("smoother") == args.smoother and world == 1 and ent.get("kernel", "").split("<")[0] == launched_kernel.split("<")[0]:
+                traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "level-0 smoother sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "peak_kind": peak_kind, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": f"level-0 smoother sweep ({launched_kernel})", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "peak_kind": peak_kind, "traffic": traffic, "traffic_source": traffic_src,
                 "alg_bytes_per_launch": ALG_BYTES_SWEEP_3D * nvox * sweeps / max(sm_launches, 1),
                 "launches": sm_launches, "ms_per_launch": sm_ms / max(sm_launches, 1),
                 "dram_bytes_per_voxel": (traffic / nvox) if traffic else None,
+                "frac_on_dram_bytes": (traffic / (sm_ms / max(sm_launches, 1) * 1e-3) / 1e9 / peak) if traffic and sm_ms > 0 else None,
                 "note": "achieved counts the canonical 36 B per voxel and sweep; the Gauss-Seidel sweep reads pre-evaluated fp16 operator "
-                        "rows (20 B) instead of the six fp32 tensor planes (24 B), so its DRAM traffic is 32 B per voxel and frac can pass 1",
+                        "rows (20 B) instead of the six fp32 tensor planes (24 B), so its DRAM traffic is 32 B per voxel and frac can pass 1 "
+                        "(frac_on_dram_bytes = the ncu-measured bytes over the same event time)",
                 "share_of_step": sm_ms / dev_ms if dev_ms > 0 else None,
                 "class_ms_per_cycle": {k: v / args.steps for k, v in st["prof_ms"].items() if v > 0},
                 "class_launches_per_cycle": {k: v / args.steps for k, v in st["prof_launches"].items() if v > 0},
@@ -409,6 +511,7 @@ def run_ours(args):
 
     # ---- e2e: the filter call with host (pinned) buffers ----
     e2e = None
+    img_np = None
     if args.e2e_reps > 0:
         T_h = torch.empty(shape + (6,), dtype=torch.float32, pin_memory=True)
         T_h.copy_(phantom.planes_to_aos(D))
@@ -443,17 +546,48 @@ def run_ours(args):
                "call": "SetDiffusionTensor(host fp32 AoS) + solve(host fp32 image): 4 time steps to relres 1e-10",
                "cycles_per_call": cycles, "s_per_call": dt, "s_per_call_all_reps": [round(t, 4) for t in times], "cycles_per_step": s.last_stats["cycles_per_step"],
                "final_relres": max(s.last_stats["final_relres"]), "setup_ms": s.last_stats["setup_ms"],
-               "h2d_ms": s.last_stats["h2d_ms"], "d2h_ms": s.last_stats["d2h_ms"]}
+               "h2d_ms": s.last_stats["h2d_ms"], "d2h_ms": s.last_stats["d2h_ms"], "graph_launches": s.last_stats.get("graph_launches")}
+        del T_h, out_h, T_np, out_np
+    elif args.ved and world == 1:
+        img_np = img.cpu().numpy()
     s.close()
+    del img
+    D = None
+    torch.cuda.empty_cache()
 
-    # ---- optional: the whole VED filter (front-end + DiffusionStep) through the filter call, host buffers ----
+    # ---- the whole VED filter (tensor front-end on the device + DiffusionStep) through the filter call, host buffers ----
     ved = None
     if args.ved and world == 1:
         try:
-            ved = run_ved_filter(args, img_h.numpy() if args.e2e_reps > 0 else img.cpu().numpy(), local_rank)
+            ved = run_ved_filter(args, img_np, local_rank)
             launches_timed += ved.pop("_launches", 0)
         except Exception as e:  # noqa: BLE001 -- an extra, never the headline
             ved = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- N > 1: parity of the z-slab path with the single-GPU solve, on this run's GPUs ----
+    parity = None
+    if slab_mode and not args.no_slab_parity:
+        try:
+            parity = slab_parity(rank, world, local_rank, dev, want_peer and peer_halo)
+        except Exception as e:  # noqa: BLE001
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+
+    # ---- N = 8 (or --weak): BASELINE.json configs[4], 1024^3 on 8 GPUs, next to 512^3 on ONE GPU of the same box in the same run ----
+    extra = None
+    if slab_mode and (world == 8 or args.weak) and args.size == 512:
+        try:
+            wshape = (1024, 1024, 1024) if world == 8 else (512 * world, 512, 512)
+            w = extra_volume_run(wshape, args, smoother, rank, world, local_rank, dev, want_peer and peer_halo, barrier)
+            barrier()
+            one = extra_volume_run((512, 512, 512), args, smoother, 0, 1, local_rank, dev, False, lambda: torch.cuda.synchronize(), active=rank == 0)
+            barrier()
+            if rank == 0:
+                w["vs_n1"] = w["value"] / one["value"]
+                w["n1_same_run"] = one
+                w["target"] = "BASELINE.json north_star: >= 6x one GPU at 512^3 for 1024^3 on 8 GPUs (same work per GPU)"
+            extra = {"weak_1024" if world == 8 else f"weak_512x512x{512 * world}": w}
+        except Exception as e:  # noqa: BLE001
+            extra = {"weak_1024": {"error": f"{type(e).__name__}: {e}"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -471,10 +605,13 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if (slab_mode or world == 1) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, f"z-slabs: {world} x {shape[0]} planes, halo = " + ("NVLink peer stores from the producing kernels + stream memory ops"
-                                      if peer_halo else "NCCL send/recv per sweep") + ", levels <= 64^3 agglomerated on rank 0"
+                                      if peer_halo else "NCCL send/recv per sweep") + ", coarse levels agglomerated on rank 0"
                                       if slab_mode else "independent replicas (one volume per GPU)" if world > 1 else "single GPU"),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ved_filter": ved, "gpu_launches": int(launches_timed), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ved_filter": ved, "slab_parity": parity, "extra": extra,
+            "gpu_launches": int(launches_timed), "clocks": clocks,
             "relres_after_timed_cycles": float(relres[-1]) if len(relres) else None, "wall_ms_timed_region": wall_ms,
+            "timed_iterate": "the timed cycles continue from the warm-up cycles' iterate (tolerance 0: the loop never stops early); every kernel "
+                             "of a cycle does the same work whatever the residual, so the time per cycle does not depend on it",
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -498,7 +635,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: keep the NCCL send/recv halo exchange instead of peer stores")
     ap.add_argument("--peer-halo", action="store_true", help="N > 4: use the peer-memory halo too (default only up to 4 ranks)")
-    ap.add_argument("--ved", action="store_true", help="N = 1: also time the whole VED filter (tensor front-end + diffusion) through the filter call")
+    ap.add_argument("--ved", dest="ved", action="store_true", default=True, help="N = 1: also time the whole VED filter (tensor front-end + diffusion) through the filter call (default)")
+    ap.add_argument("--no-ved", dest="ved", action="store_false")
+    ap.add_argument("--no-slab-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU parity solves after the timed region")
+    ap.add_argument("--weak", action="store_true", help="N > 1: also run the weak-scaling volume (512 x 512 x 512N; 1024^3 at N = 8 is always run)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent volumes per GPU instead of z-slabs of one volume")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

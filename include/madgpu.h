@@ -93,6 +93,7 @@ typedef struct madgpu_stats {
   /* profiling (madgpu_set_profiling(ctx,1)): device ms and launch counts by kernel class          */
   double prof_ms[16];
   int64_t prof_launches[16];
+  int64_t graph_launches;                     /* CUDA-graph replays of the captured coarse part of a cycle (their kernels are counted in kernel_launches) */
 } madgpu_stats;
 
 /* kernel classes for prof_ms / prof_launches */
@@ -104,6 +105,7 @@ typedef struct madgpu_stats {
 #define MADGPU_K_COARSE 5      /* coarsest-grid solve                          */
 #define MADGPU_K_MISC 6        /* fills, casts, axpy                           */
 #define MADGPU_K_HALO 7        /* halo exchange (multi-GPU)                    */
+#define MADGPU_K_GRAPH 8       /* captured coarse part of a V-cycle (CUDA graph): every class of the levels <= 128^3 voxels */
 
 void madgpu_params_default(madgpu_params *p);
 

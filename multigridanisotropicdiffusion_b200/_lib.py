@@ -18,7 +18,7 @@ CYCLE_V, CYCLE_FMG, CYCLE_SMOOTHER = 0, 1, 2
 PIX_U8, PIX_I16, PIX_F32, PIX_F64 = 0, 1, 2, 3
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ESINGULAR, ENUMERIC = 0, -1, -2, -3, -4, -5, -6
 
-K_NAMES = ["smooth0", "smoothc", "resid0", "restrict", "prolong", "coarse", "misc", "halo"]
+K_NAMES = ["smooth0", "smoothc", "resid0", "restrict", "prolong", "coarse", "misc", "halo", "graph"]
 
 
 class Params(C.Structure):
@@ -60,6 +60,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int64),
         ("prof_ms", C.c_double * 16),
         ("prof_launches", C.c_int64 * 16),
+        ("graph_launches", C.c_int64),
     ]
 
 

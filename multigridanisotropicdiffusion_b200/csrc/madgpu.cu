@@ -138,8 +138,22 @@ struct madgpu_ctx {
   int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
-  int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 (opt-in tuning hook, MADGPU_RES64_COEF32)
+  int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 -- the row the fp32 sweeps relax -- and applied in fp64 (default; MADGPU_RES64_COEF32=0: fp64 row)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
+  // CUDA graphs of the launch-bound part of a V-cycle: vcycle(l) for the first level of at most graph_voxels voxels (and with it
+  // everything below) is captured once per (level, zero guess, solver settings, ping-pong state) and replayed
+  struct CycleGraph {
+    int level, zero_guess, smoother, nu;
+    double omega;
+    std::vector<const void*> state;  // u pointers of levels >= level at entry (the sweeps swap u / tmp)
+    cudaGraphExec_t exec;
+    int launches, seen;
+    bool bad;
+  };
+  std::vector<CycleGraph> graphs;
+  long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
+  int prolong_cell;        // MADGPU_PROLONG_CELL=0: keep the generic streaming prolongation for cell-centred transfers too (A/B hook)
+  bool capturing;
 };
 
 namespace {
@@ -720,9 +734,18 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
   if constexpr (std::is_same<TO, float>::value) {
     if (use_fast(ctx, F)) {
       constexpr int WY = 8;
-      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, (F.g.nz + fast::PROLONG_ZB - 1) / fast::PROLONG_ZB);
       Geom gg = F.g;
       set_ghosts(ctx, gg, F, fine, sizeof(float));
+      if (C.cent[0] == 1 && C.cent[1] == 1 && C.cent[2] == 1 && ctx->prolong_cell) {
+        // cell-centred along all axes (power-of-two volumes): the blocked kernel, one coarse plane loaded per two fine planes
+        const int gx = (F.g.nx + fast::TX - 1) / fast::TX, gy = (C.g.ny + WY - 1) / WY;
+        const int chunks = std::max(1, std::min(C.g.nz, (148 * 8 + gx * gy - 1) / (gx * gy)));
+        const int zcc = (C.g.nz + chunks - 1) / chunks;
+        MAD_LAUNCH((fast::k_fast_prolong_cell<ADD, WY>), dim3(gx, gy, (C.g.nz + zcc - 1) / zcc), dim3(32, WY), 0, ctx->stream, C.g, gg, coarse, fine, zcc);
+        halo_signal(ctx, fine);
+        return;
+      }
+      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, (F.g.nz + fast::PROLONG_ZB - 1) / fast::PROLONG_ZB);
       MAD_LAUNCH((fast::k_fast_prolong<ADD, WY>), fg, dim3(32, WY), 0, ctx->stream, C.g, gg, transfer_of(C), coarse, fine);
       halo_signal(ctx, fine);
       return;
@@ -763,11 +786,7 @@ void op_coarse_solve(madgpu_ctx* ctx)
   }
 }
 
-// V-cycle at level l on (L.u, L.f): itkMultigridAnisotropicDiffusionImageFilter.hxx:341-493 without the
-// reference's logging-only residual/norm passes (:389-411, :437-439, :464-487).
-// zero_guess: the iterate of level l is identically zero on entry and need not have been written (the correction
-// equations of the coarser levels, …Filter.hxx:415-416, and of level 0 in defect-correction form).
-void vcycle(madgpu_ctx* ctx, int l, bool zero_guess)
+void vcycle_body(madgpu_ctx* ctx, int l, bool zero_guess)
 {
   if (l == ctx->nlevels - 1) {  // :356-371  (both solvers overwrite the whole iterate)
     if (ctx->world > 1) agglomerated_solve(ctx);
@@ -783,6 +802,89 @@ void vcycle(madgpu_ctx* ctx, int l, bool zero_guess)
   vcycle(ctx, l + 1, true);                               // :415-420, zero coarse guess
   op_prolong<float, true>(ctx, l, C.u, L.u);              // :422-435
   op_smooth(ctx, l, ctx->p.smoother, nu);                 // :460-463
+}
+
+void drop_graphs(madgpu_ctx* ctx)
+{
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();
+}
+
+// The coarse part of a cycle is dozens of launches of a few microseconds each (66 of the 96 launches of a 512^3 cycle): from the
+// first level of at most graph_voxels voxels down it is captured into a CUDA graph -- every shape, pointer and loop count below
+// that level is static between two tensors -- and replayed with one launch.  The first call with a given key runs uncaptured
+// (it builds the packed rows of the levels, which allocates), the second is captured.  Single-context levels only: a z-slab
+// context keeps its distributed levels outside (stream memory operations, NCCL), its serial sub-hierarchy on rank 0 qualifies.
+bool vcycle_graphed(madgpu_ctx* ctx, int l, bool zero_guess)
+{
+  if (ctx->capturing || ctx->graph_voxels <= 0 || ctx->world > 1 || !ctx->coarse_direct || l == ctx->nlevels - 1) return false;
+  const Level& L = ctx->lv[l];
+  if ((long long)L.n[0] * L.n[1] * L.n[2] > ctx->graph_voxels) return false;
+  if (l > 0) {  // only the first qualifying level owns a graph; the levels below are part of it
+    const Level& P = ctx->lv[l - 1];
+    if ((long long)P.n[0] * P.n[1] * P.n[2] <= ctx->graph_voxels) return false;
+  }
+  std::vector<const void*> state;
+  for (int k = l; k < ctx->nlevels; ++k) state.push_back(ctx->lv[k].u);
+  madgpu_ctx::CycleGraph* g = nullptr;
+  for (auto& c : ctx->graphs)
+    if (c.level == l && c.zero_guess == (int)zero_guess && c.smoother == ctx->p.smoother && c.nu == ctx->p.iterations_per_grid &&
+        c.omega == ctx->p.omega && c.state == state) { g = &c; break; }
+  if (!g) {
+    if (ctx->graphs.size() >= 16) drop_graphs(ctx);  // callers that keep changing the settings: start over
+    ctx->graphs.push_back({l, (int)zero_guess, ctx->p.smoother, ctx->p.iterations_per_grid, ctx->p.omega, state, nullptr, 0, 1, false});
+    return false;  // first sight: plain launches (lazy allocations happen here)
+  }
+  if (g->bad) return false;
+  if (!g->exec) {
+    const int prof = ctx->profiling;
+    const int64_t before = ctx->launches;
+    ctx->profiling = 0;
+    ctx->capturing = true;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      vcycle_body(ctx, l, zero_guess);
+      ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr;
+    }
+    ctx->capturing = false;
+    ctx->profiling = prof;
+    g->launches = (int)(ctx->launches - before);
+    ctx->launches = before;
+    if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    // the body ran its pointer swaps on the host while capturing; they come back to the entry state after a whole cycle
+    bool same = true;
+    for (int k = l; k < ctx->nlevels; ++k) same = same && ctx->lv[k].u == state[k - l];
+    if (!ok || !same) {
+      cudaGetLastError();
+      if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+      g->bad = true;
+      if (!same) {  // cannot happen with nu pre- and nu post-sweeps; restore and run plainly
+        for (int k = l; k < ctx->nlevels; ++k)
+          if (ctx->lv[k].u != state[k - l]) std::swap(ctx->lv[k].u, ctx->lv[k].tmp);
+      }
+      return false;
+    }
+  }
+  Scope s(ctx, MADGPU_K_GRAPH, g->launches);
+  ctx->st.graph_launches++;
+  if (cudaGraphLaunch(g->exec, ctx->stream) != cudaSuccess) {
+    cudaGetLastError();
+    if (ctx->sticky.empty()) ctx->sticky = "cudaGraphLaunch of the coarse-level cycle failed";
+  }
+  return true;
+}
+
+// V-cycle at level l on (L.u, L.f): itkMultigridAnisotropicDiffusionImageFilter.hxx:341-493 without the
+// reference's logging-only residual/norm passes (:389-411, :437-439, :464-487).
+// zero_guess: the iterate of level l is identically zero on entry and need not have been written (the correction
+// equations of the coarser levels, …Filter.hxx:415-416, and of level 0 in defect-correction form).
+void vcycle(madgpu_ctx* ctx, int l, bool zero_guess)
+{
+  if (vcycle_graphed(ctx, l, zero_guess)) return;
+  vcycle_body(ctx, l, zero_guess);
 }
 
 void op_axpy(madgpu_ctx* ctx)
@@ -1078,6 +1180,7 @@ int build_coarse_solver(madgpu_ctx* ctx)
 int finish_tensor(madgpu_ctx* ctx)
 {
   for (int l = 0; l < ctx->nlevels; ++l) { ctx->lv[l].coef16_valid = false; ctx->lv[l].coef16_off = false; }
+  drop_graphs(ctx);  // the captured cycles read the packed rows of the previous tensor
   for (int l = 0; l + 1 < ctx->nlevels; ++l)
     for (int c = 0; c < ctx->ncomp; ++c)  // mad/itkGridsHierarchy.hxx:149-162
       op_restrict<float>(ctx, l, ctx->lv[l].D[c], ctx->lv[l + 1].D[c], MADGPU_K_MISC);
@@ -1389,9 +1492,14 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->p2p_drop_rank = ctx->p2p_drop_seq = -1;
     if ((e = getenv("MADGPU_P2P_TEST_DROP_SIGNAL"))) sscanf(e, "%d:%d", &ctx->p2p_drop_rank, &ctx->p2p_drop_seq);
     e = getenv("MADGPU_RES64_COEF32");
-    ctx->res64_c32 = e ? atoi(e) : 0;
+    ctx->res64_c32 = e ? atoi(e) : 1;
     e = getenv("MADGPU_FAST_CFG");
     ctx->fast_cfg = e ? atoi(e) : 0;
+    e = getenv("MADGPU_GRAPH_VOXELS");
+    ctx->graph_voxels = e ? atoll(e) : 128ll * 128 * 128;
+    ctx->capturing = false;
+    e = getenv("MADGPU_PROLONG_CELL");
+    ctx->prolong_cell = e ? atoi(e) : 1;
   }
   ctx->u64 = ctx->f64 = nullptr;
   memset(&ctx->st, 0, sizeof ctx->st);
@@ -1510,6 +1618,8 @@ void madgpu_destroy(madgpu_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->p.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (int l = 0; l < MADGPU_MAX_LEVELS; ++l)
     for (void* p : ctx->lv[l].allocs) cudaFree(p);
   for (void* p : ctx->allocs) cudaFree(p);

@@ -165,7 +165,7 @@ class MadSolver:
                  setup_ms=st.setup_ms, h2d_ms=st.h2d_ms, d2h_ms=st.d2h_ms, solve_ms=st.solve_ms, fmg_ms=st.fmg_ms,
                  kernel_launches=st.kernel_launches,
                  prof_ms={k: st.prof_ms[i] for i, k in enumerate(B.K_NAMES)},
-                 prof_launches={k: st.prof_launches[i] for i, k in enumerate(B.K_NAMES)})
+                 prof_launches={k: st.prof_launches[i] for i, k in enumerate(B.K_NAMES)}, graph_launches=int(st.graph_launches))
         self.last_stats = d
         return d
 

@@ -10,6 +10,8 @@
 #include <sys/mman.h>
 
 #include <chrono>
+#include <functional>
+#include <vector>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -38,8 +40,14 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
-struct FakeStream { int unused; };
-typedef FakeStream* cudaStream_t;  // in-order and synchronous
+// in-order and synchronous; while a capture is open (cudaStreamBeginCapture) launches, memsets and copies are recorded as closures
+// with their arguments by value -- the semantics of a CUDA graph -- instead of being run
+struct FakeStream { std::vector<std::function<void()>>* rec = nullptr; };
+typedef FakeStream* cudaStream_t;
+struct FakeGraph { std::vector<std::function<void()>> ops; };
+typedef FakeGraph* cudaGraph_t;
+typedef FakeGraph* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
 struct FakeEvent { std::chrono::steady_clock::time_point t; };
 typedef FakeEvent* cudaEvent_t;
 enum { cudaStreamNonBlocking = 1 };
@@ -131,7 +139,34 @@ inline cudaError_t cudaFree(void* p)
   __atomic_sub_fetch(&g_live_allocs, 1, __ATOMIC_RELAXED);
   return cudaSuccess;
 }
-inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t s)
+{
+  if (s && s->rec) s->rec->push_back([=] { std::memmove(dst, src, bytes); });
+  else std::memmove(dst, src, bytes);
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode)
+{
+  if (!s || s->rec) return cudaErrorInvalidValue;
+  s->rec = new std::vector<std::function<void()>>();
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g)
+{
+  if (!s || !s->rec) return cudaErrorInvalidValue;
+  *g = new FakeGraph{std::move(*s->rec)};
+  delete s->rec;
+  s->rec = nullptr;
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) { *e = new FakeGraph(*g); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t)
+{
+  for (auto& op : e->ops) op();
+  return cudaSuccess;
+}
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = new FakeStream(); return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
@@ -147,7 +182,12 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
 
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { std::memmove(dst, src, bytes); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { std::memset(p, v, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t s)
+{
+  if (s && s->rec) s->rec->push_back([=] { std::memset(p, v, bytes); });
+  else std::memset(p, v, bytes);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
 {
   for (size_t r = 0; r < height; ++r) std::memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);

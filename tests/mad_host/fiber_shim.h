@@ -303,7 +303,10 @@ T shuffle(T v, int src)
 #define MAD_LAUNCH(kernel, grid, block, smem, stream, ...)                                                                   \
   do {                                                                                                                      \
     if (mad_host::trace()) std::fprintf(stderr, "mad_host: launch %s\n", #kernel);                                          \
-    mad_host::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { MAD_UNPAREN kernel(__VA_ARGS__); });                     \
+    if ((stream) && (stream)->rec) /* stream capture: record the launch with its arguments by value, run it at cudaGraphLaunch */ \
+      (stream)->rec->push_back([=] { mad_host::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { MAD_UNPAREN kernel(__VA_ARGS__); }); }); \
+    else                                                                                                                    \
+      mad_host::launch(dim3(grid), dim3(block), (size_t)(smem), [&] { MAD_UNPAREN kernel(__VA_ARGS__); });                   \
   } while (0)
 
 // csrc/ved_kernels.cuh launches through VED_LAUNCH (no dynamic shared memory)

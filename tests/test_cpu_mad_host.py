@@ -110,6 +110,35 @@ def test_diagonal_beyond_the_packed_range_falls_back_or_fails_loudly(MadSolver, 
         assert s.gs_tile(0)[1] == 4
 
 
+@pytest.mark.parametrize("smoother,cycle", [("gs", 0), ("wj", 0), ("gs", 1)])
+def test_captured_coarse_cycle_is_the_same_cycle(MadSolver, monkeypatch, smoother, cycle):
+    """The launch-bound part of a V-cycle (levels of <= 128^3 voxels) is captured into a CUDA graph on its second use and replayed.
+    Same kernels, same arguments: the solve must be bit-identical to the one with graphs switched off (MADGPU_GRAPH_VOXELS=0)."""
+    monkeypatch.setenv("MADGPU_FAST_MIN_NX", "8")
+    sm = 1 if smoother == "wj" else 0
+    shape, sp = (12, 16, 64), (0.3125, 0.3125, 0.5)
+    T, img = random_spd_tensor(shape, seed=2), random_image(shape, seed=5)
+    outs, stats = [], []
+    for voxels in ("0", None):
+        if voxels is None:
+            monkeypatch.delenv("MADGPU_GRAPH_VOXELS")
+        else:
+            monkeypatch.setenv("MADGPU_GRAPH_VOXELS", voxels)
+        with MadSolver(shape, sp, time_step=0.1, smoother=sm, iterations_per_grid=2, cycle=cycle, tolerance=1e-8, max_cycles=40, number_of_steps=2) as s:
+            s.set_tensor(T)
+            outs.append(s.solve(img, out_dtype=np.float64))
+            stats.append(s.last_stats)
+            s.set_tensor(T * np.float32(1.5))  # a new tensor drops the graphs (they read the packed rows of the old one)
+            outs.append(s.solve(img, out_dtype=np.float64))
+            stats.append(s.last_stats)
+    assert stats[0]["graph_launches"] == 0 and stats[1]["graph_launches"] == 0
+    assert stats[2]["graph_launches"] >= stats[2]["total_cycles"] - 2 and stats[3]["graph_launches"] >= stats[3]["total_cycles"] - 2
+    for a, b in ((0, 2), (1, 3)):
+        assert stats[a]["cycles_per_step"] == stats[b]["cycles_per_step"] and stats[a]["kernel_launches"] == stats[b]["kernel_launches"]
+        assert np.array_equal(outs[a], outs[b])
+    assert not np.array_equal(outs[0], outs[1])
+
+
 def test_operators_and_casts(MadSolver):
     """Per-operator entry points on a mixed-centring hierarchy, FMG, smoother-only mode, integer pixels."""
     shape, sp = (14, 25, 12), (0.33, 0.33, 0.33)

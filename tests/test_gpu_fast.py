@@ -81,15 +81,21 @@ def test_fast_residual_and_norm(case, fast_env):
     s.close()
 
 
+@pytest.mark.parametrize("rows", ["fp32", "fp64"])
 @pytest.mark.parametrize("case", CASES)
-def test_fast_residual_f64(case, fast_env):
+def test_fast_residual_f64(case, fast_env, rows, monkeypatch):
+    """The level-0 stop-test / defect residual of the solve loop (streaming kernel, fp32 r + fp64 norm).  Default: the operator row
+    is evaluated in fp32 -- bit for bit the row the fp32 sweeps relax -- and APPLIED in fp64 to the fp64 iterate, so the norm agrees
+    with the all-fp64 oracle to the rounding of the row (~1e-7 relative; what the fp32 storage of the tensor costs as well).
+    MADGPU_RES64_COEF32=0 evaluates the row in fp64 too: 1e-12."""
+    monkeypatch.setenv("MADGPU_RES64_COEF32", "1" if rows == "fp32" else "0")
     s, o = _mk(case)
     shp = s.levels[0]["shape"]
     u, f = random_image(shp, seed=3).astype(np.float64), random_image(shp, seed=4).astype(np.float64)
-    # norm_only runs the kernel of the solve loop (streaming, fp32 r + fp64 norm)
+    # norm_only runs the kernel of the solve loop
     _, nrm = s.op_residual_f64(u, f, norm_only=True)
     r = o.residual(0, u, f)
-    assert abs(nrm - np.linalg.norm(r)) < 1e-12 * np.linalg.norm(r)
+    assert abs(nrm - np.linalg.norm(r)) < (2e-6 if rows == "fp32" else 1e-12) * np.linalg.norm(r)
     s.close()
 
 
@@ -201,7 +207,10 @@ def test_fused_gs_converged_image(case, gs_env):
     assert max(st["cycles_per_step"][:2]) <= max(cyc) + 2, (st["cycles_per_step"], cyc)
 
 
-@pytest.mark.parametrize("case", CASES + [((20, 22, 260), (1.0, 1.0, 1.0), 0.1), ((17, 19, 257), (1.0, 1.0, 1.0), 0.1)])
+@pytest.mark.parametrize("case", CASES + [((20, 22, 260), (1.0, 1.0, 1.0), 0.1), ((17, 19, 257), (1.0, 1.0, 1.0), 0.1),
+                                  # all axes cell-centred (k_fast_prolong_cell): odd coarse row length / a last thread with 2 of 4 voxels,
+                                  # a row that ends exactly with a thread, two warp columns
+                                  ((12, 14, 134), (1.0, 1.0, 1.0), 0.1), ((8, 12, 132), (1.0, 1.0, 1.0), 0.1), ((16, 24, 264), (1.0, 1.0, 1.0), 0.1)])
 def test_fast_restriction_and_prolongation(case, fast_env):
     """Streaming transfer kernels (4 fine voxels per thread) against the oracle, every centring combination."""
     from oracle import oracle as O
