@@ -459,6 +459,101 @@ __global__ void __launch_bounds__(256) k_coarse_gemv(Geom g, const double* __res
   }
 }
 
+// ---- dense inverse of the coarsest-grid operator, built on the device (replaces the vnl_sparse_lu factorisation of
+// ---- mad/itkDirectSolver.hxx:44-86; a host LU of 512 unknowns cost 50-300 ms per tensor, this costs a few) -----------------
+// M = [A | I], row-major, leading dimension ld = 2n, zero-initialised by the caller.  Row = LexPosition (mad/itkDirectSolver.h:89-99).
+template <int DIM>
+__global__ void k_coarse_matrix(Geom g, Tensor D, double* __restrict__ M, int n, int ld)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const int x = row % g.nx, y = (row / g.nx) % g.ny, z = row / (g.nx * g.ny);
+  Row<double> r;
+  row_coeffs<DIM, double>(g, D, x, y, z, r);
+  double S[DIM == 2 ? 9 : 27];
+  scatter_row<DIM, double>(g, r, x, y, z, S);
+  const int zl = DIM == 3 ? -1 : 0, zh = DIM == 3 ? 1 : 0;
+  double* m = M + (size_t)row * ld;
+  for (int oz = zl; oz <= zh; ++oz)
+    for (int oy = -1; oy <= 1; ++oy)
+      for (int ox = -1; ox <= 1; ++ox) {
+        const int xx = x + ox, yy = y + oy, zz = z + oz;
+        if (xx < 0 || xx >= g.nx || yy < 0 || yy >= g.ny || zz < 0 || zz >= g.nz) continue;  // folded onto the mirror by scatter_row
+        const int si = DIM == 2 ? (oy + 1) * 3 + (ox + 1) : ((oz + 1) * 3 + (oy + 1)) * 3 + (ox + 1);
+        m[((size_t)zz * g.ny + yy) * g.nx + xx] = S[si];
+      }
+  m[n + row] = 1.0;
+}
+
+// Gauss-Jordan step k, part 1 (one block): partial pivoting over rows k..n-1 of column k, row swap, pivot row scaled to a unit
+// pivot, column k saved to colk[] (the elimination overwrites it).  singular[0] is set when no pivot is left.
+__global__ void __launch_bounds__(1024) k_gj_pivot(double* __restrict__ M, int n, int ld, int k, double* __restrict__ colk, int* __restrict__ singular)
+{
+  __shared__ double sv[32];
+  __shared__ int si[32];
+  __shared__ int prow;
+  __shared__ double pinv;
+  const int tid = threadIdx.x;
+  double best = -1.0;
+  int bi = k;
+  for (int i = k + tid; i < n; i += blockDim.x) {
+    const double v = fabs(M[(size_t)i * ld + k]);
+    if (v > best) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { sv[tid >> 5] = best; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid < 32) {
+    best = tid < (int)((blockDim.x + 31) >> 5) ? sv[tid] : -1.0;
+    bi = tid < (int)((blockDim.x + 31) >> 5) ? si[tid] : k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (tid == 0) {
+      prow = bi;
+      if (!(best > 0.0)) { singular[0] = 1; pinv = 0.0; }
+      else pinv = 1.0 / M[(size_t)bi * ld + k];
+    }
+  }
+  __syncthreads();
+  const int p = prow;
+  const double inv = pinv;
+  double* rk = M + (size_t)k * ld;
+  double* rp = M + (size_t)p * ld;
+  for (int j = tid; j < ld; j += blockDim.x) {
+    const double a = rk[j], b = rp[j];
+    rk[j] = b * inv;
+    if (p != k) rp[j] = a;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) colk[i] = i == k ? 0.0 : M[(size_t)i * ld + k];
+}
+
+// part 2: rows i != k lose their column-k entry, M[i][:] -= colk[i] * M[k][:].  grid = (ceil(ld/256), ceil(n/8)), block = 256
+__global__ void __launch_bounds__(256) k_gj_eliminate(double* __restrict__ M, int n, int ld, int k, const double* __restrict__ colk)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ld) return;
+  const double pk = M[(size_t)k * ld + j];
+  const int i0 = blockIdx.y * 8;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = i0 + r;
+    if (i < n && i != k) {
+      const double c = colk[i];
+      if (c != 0.0) M[(size_t)i * ld + j] -= c * pk;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Element-wise helpers (pitched <-> dense, casts, axpy).
 // ------------------------------------------------------------------------------------------

@@ -27,6 +27,10 @@ def load():
     """The host build with the argtypes of the real binding; call bind() to make MadSolver use it."""
     from multigridanisotropicdiffusion_b200 import _lib as B
     build()
+    # the device-side Gauss-Jordan inverse of the coarsest operator is ~2 n kernel launches of n x 2n threads: minutes on fibres for
+    # the 512-unknown grids most tests end with.  The emulated runs keep the host LU (same inverse to rounding) unless a test asks
+    # for the device path explicitly (tests/test_cpu_mad_host.py::test_device_inverse_of_the_coarsest_operator).
+    os.environ.setdefault("MADGPU_COARSE_HOST", "1")
     real = B.load()
     L = C.CDLL(HOST_LIB)
     for name in B.EXPORTS:

@@ -139,6 +139,24 @@ def test_captured_coarse_cycle_is_the_same_cycle(MadSolver, monkeypatch, smoothe
     assert not np.array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("shape,sp", [((12, 14, 12), (0.3125, 0.3125, 0.5)), ((13, 12), (0.7, 1.3))])
+def test_device_inverse_of_the_coarsest_operator(MadSolver, monkeypatch, shape, sp):
+    """The coarsest-grid direct solver (mad/itkDirectSolver.hxx:32-147): operator assembled and inverted on the device (k_coarse_matrix,
+    Gauss-Jordan with partial pivoting) against the oracle's dense LU, and against the host LU path it replaced."""
+    T = random_spd_tensor(shape, seed=4)
+    o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=1, nu=2)
+    res = {}
+    for host in ("0", "1"):
+        monkeypatch.setenv("MADGPU_COARSE_HOST", host)
+        with MadSolver(shape, sp, time_step=0.1, smoother=1, iterations_per_grid=2) as s:
+            s.set_tensor(T)
+            fl = random_image(s.levels[-1]["shape"], seed=3)
+            res[host] = s.op_coarse_solve(fl)
+    ref = o.direct_solve(fl.astype(np.float64))
+    assert rel_l2(res["0"], ref) < 1e-6 and rel_l2(res["1"], ref) < 1e-6
+    assert rel_l2(res["0"], res["1"]) < 1e-6
+
+
 def test_operators_and_casts(MadSolver):
     """Per-operator entry points on a mixed-centring hierarchy, FMG, smoother-only mode, integer pixels."""
     shape, sp = (14, 25, 12), (0.33, 0.33, 0.33)
