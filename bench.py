@@ -434,14 +434,12 @@ def run_ours(args):
         z0, z1 = slabs.slab_range(n, rank, world)
         img, D = phantom.vessel_phantom(shape, device=dev, z_range=(z0, z1))
         torch.cuda.synchronize()
-        want_peer = not args.nccl_halo and (world <= 4 or args.peer_halo or os.environ.get("MADGPU_BENCH_PEER8") == "1")
-        if want_peer and world > 4:
-            # beyond the rank counts verified on hardware: arrival counters awaited by the bounded k_halo_wait, so that a signal that
-            # never arrives costs a time-out and an error on every rank (handled below) instead of a hung stream
-            os.environ["MADGPU_P2P_WAIT"] = "kernel"
-            os.environ.setdefault("MADGPU_P2P_TIMEOUT_MS", "3000")
+        want_peer = not args.nccl_halo
+        # arrival counters are awaited by the bounded k_halo_wait (the library's default): a signal that never arrives costs a
+        # time-out and an error on every rank -- caught by the trial cycles below -- instead of a hung stream
+        os.environ.setdefault("MADGPU_P2P_TIMEOUT_MS", "3000")
         s, peer_halo = make_slab_solver(shape, smoother, nu, local_rank, rank, world, want_peer, tolerance=0.0, max_cycles=1 << 20)
-        if peer_halo and world > 4:
+        if peer_halo:
             # trial cycles: a time-out is reported by every rank in the same cycle (the flag travels with the norm all-reduce)
             try:
                 s.set_tensor_device([D[c].data_ptr() for c in range(6)])
@@ -451,7 +449,6 @@ def run_ours(args):
                 if rank == 0:
                     print(f"bench.py: peer-memory halo failed on {world} ranks ({e}); falling back to the NCCL halo", file=sys.stderr, flush=True)
                 s.close()
-                os.environ["MADGPU_P2P_WAIT"] = "memop"
                 want_peer = False
                 s, peer_halo = make_slab_solver(shape, smoother, nu, local_rank, rank, world, False, tolerance=0.0, max_cycles=1 << 20)
     else:
@@ -634,7 +631,7 @@ def main():
     ap.add_argument("--e2e-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="N > 1: keep the NCCL send/recv halo exchange instead of peer stores")
-    ap.add_argument("--peer-halo", action="store_true", help="N > 4: use the peer-memory halo too (default only up to 4 ranks)")
+    ap.add_argument("--peer-halo", action="store_true", help="(default since round 2: the peer-memory halo is used at every N unless --nccl-halo)")
     ap.add_argument("--ved", dest="ved", action="store_true", default=True, help="N = 1: also time the whole VED filter (tensor front-end + diffusion) through the filter call (default)")
     ap.add_argument("--no-ved", dest="ved", action="store_false")
     ap.add_argument("--no-slab-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU parity solves after the timed region")

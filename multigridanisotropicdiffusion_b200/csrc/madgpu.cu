@@ -121,7 +121,7 @@ struct madgpu_ctx {
   uint32_t* flags_hi;     // the upper neighbour's flags (mapped), we write [0]
   uint32_t halo_seq;      // number of fields produced so far (identical on every rank: same program order)
   bool p2p;
-  int p2p_wait_kernel;          // MADGPU_P2P_WAIT=kernel: arrival counters are awaited by k_halo_wait (bounded) instead of cuStreamWaitValue32
+  int p2p_wait_kernel;          // arrival counters are awaited by k_halo_wait (bounded; default) or, MADGPU_P2P_WAIT=memop, by cuStreamWaitValue32
   long long p2p_timeout_cycles; // MADGPU_P2P_TIMEOUT_MS (default 10 s at ~2 GHz)
   int p2p_drop_rank, p2p_drop_seq;  // test hook MADGPU_P2P_TEST_DROP_SIGNAL=rank:seq: from that sequence number on the rank's signals are not sent
   int rank, world;
@@ -1521,7 +1521,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     e = getenv("MADGPU_GS_FUSED");
     ctx->gs_fused = e ? atoi(e) : 1;
     e = getenv("MADGPU_P2P_WAIT");
-    ctx->p2p_wait_kernel = e && !strcmp(e, "kernel");
+    ctx->p2p_wait_kernel = !(e && !strcmp(e, "memop"));  // default: bounded k_halo_wait (verified on 2 and 8 B200); "memop": cuStreamWaitValue32
     e = getenv("MADGPU_P2P_TIMEOUT_MS");
     ctx->p2p_timeout_cycles = (long long)((e ? atof(e) : 10000.0) * 2.0e6);
     ctx->p2p_drop_rank = ctx->p2p_drop_seq = -1;
