@@ -212,6 +212,13 @@ int madgpu_level_info(const madgpu_ctx *ctx, int32_t level, int32_t size[3], dou
  * then odd rows; values outside the tile are those of the previous sweep. */
 int madgpu_gs_tile(const madgpu_ctx *ctx, int32_t level, int32_t tile[3]);
 
+/* The passes the NEXT n_iter Gauss-Seidel sweeps of a leg on `level` will be run as (no reference counterpart: the reference runs
+ * n_iter lexicographic sweeps, mad/itkMultigridGaussSeidelSmoother.hxx:33-111).  Six values per pass: {sweeps fused in the pass,
+ * tile x, tile y, tile z, tile-grid shift y, shift z}.  A pass that fuses S > 1 sweeps (temporal blocking) runs S sweeps of the
+ * ordering above inside every tile with the values outside the tile frozen at those the pass started from; the tile of voxel
+ * (y, z) is ((y + shift y) / tile y, (z + shift z) / tile z).  Returns the number of passes, or a negative error. */
+int madgpu_gs_leg_plan(const madgpu_ctx *ctx, int32_t level, int32_t n_iter, int32_t *passes, int32_t capacity);
+
 /* ---- per-operator entry points (isolated parity tests; HOST dense fp32 buffers of the level's size) ---- */
 /* restricted tensor planes of a level: ncomp * nvox floats, SoA (mad/itkGridsHierarchy.hxx:149-162) */
 int madgpu_op_get_tensor(madgpu_ctx *ctx, int32_t level, float *planes);

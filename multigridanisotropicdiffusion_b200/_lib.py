@@ -98,7 +98,7 @@ EXPORTS = [
     "madgpu_set_tensor_f32", "madgpu_set_tensor_f64", "madgpu_set_tensor_device_f32", "madgpu_solve_cast",
     "madgpu_solve_u8", "madgpu_solve_i16", "madgpu_solve_f32", "madgpu_solve_f64", "madgpu_solve_device_f32",
     "madgpu_cycles_begin_device_f32", "madgpu_cycles_begin_f32", "madgpu_cycles_run",
-    "madgpu_cycles_end_device_f32", "madgpu_cycles_end_f64", "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info", "madgpu_gs_tile",
+    "madgpu_cycles_end_device_f32", "madgpu_cycles_end_f64", "madgpu_get_relres_history", "madgpu_set_profiling", "madgpu_num_levels", "madgpu_level_info", "madgpu_gs_tile", "madgpu_gs_leg_plan",
     "madgpu_op_get_tensor", "madgpu_op_assemble", "madgpu_op_smooth", "madgpu_op_residual",
     "madgpu_op_residual_f64", "madgpu_op_restrict", "madgpu_op_prolong", "madgpu_op_coarse_solve",
     "madgpu_op_vcycle", "madgpu_fetch_output",
@@ -145,6 +145,7 @@ def load() -> C.CDLL:
     L.madgpu_get_relres_history.argtypes = [vp, C.POINTER(f64), i32]
     L.madgpu_set_profiling.argtypes = [vp, i32]
     L.madgpu_gs_tile.argtypes = [vp, i32, C.POINTER(i32)]
+    L.madgpu_gs_leg_plan.argtypes = [vp, i32, i32, C.POINTER(i32), i32]
     L.madgpu_create_slab.argtypes = [C.POINTER(Params), C.c_char_p, C.POINTER(vp)]
     L.madgpu_nccl_unique_id.argtypes = [C.c_char_p]
     L.madgpu_slab.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]

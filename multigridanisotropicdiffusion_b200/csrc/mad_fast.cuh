@@ -983,6 +983,200 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Temporal blocking: S Gauss-Seidel sweeps of a V-cycle leg in ONE pass over the volume (k_coef_gs_tb).
+//
+// A sweep of k_coef_gs2 moves exactly the bytes it has to (32 B per voxel: u, f, packed rows, u') at ~0.87 of the copy
+// bandwidth, so the nu sweeps of a leg can only get faster by not moving u, f and the rows nu times.  Here the CTA keeps a
+// ring of 2S+2 planes of its tile of u in SHARED MEMORY (tile = 128 x 2*WP rows, plus a frozen one-voxel halo), fed one plane
+// per step by cp.async, and runs the S sweeps as a software pipeline along z: at step t sweep s relaxes plane t - 2s.  The lag
+// of two planes makes the planes written in a step (t, t-2, ...) disjoint from the planes read from other sweeps (t+-1, t-2+-1,
+// ...), so all sweeps share the two phases of a step (even rows, odd rows -- the in-plane colouring of k_coef_gs2) and the CTA
+// synchronises twice per step however many sweeps are fused.  Inside the tile the result is exactly S sequential sweeps in the
+// documented order; values OUTSIDE the tile (the halo rows / columns, the planes below and above the z chunk, the ghost planes
+// of a z-slab) stay those of the array the pass started from for all S sweeps ("frozen halo").  That is a weaker smoother at
+// the tile faces than S separate sweeps, which see the neighbours' previous sweep; the host therefore SHIFTS the tile grid by
+// half a tile in y and z between consecutive passes, so the faces of one leg lie in the interior of the next leg's tiles
+// (tools/gs_order_experiment.py and tests: same cycle counts as separate sweeps on the reference's volume).  All orderings share
+// the fixed point A u = f; Gauss-Seidel parity is stated on the converged image.
+// Packed rows and f of the S planes being relaxed are re-read per sweep (L1 / L2 hits: a plane is reused two and four steps
+// after its first touch), u is read from HBM once and written once per pass: ~32 B per voxel for S sweeps.
+// grid = (ceil(nx/128), ceil((ny+oy)/(2 WP)), ceil((nz+oz)/zc)), block = (32, WP), dynamic shared memory = tb_smem_bytes(S, WP).
+// ------------------------------------------------------------------------------------------
+constexpr int TB_ROWF = 136;  // floats per tile row: [3] = x0-1, [4..131] = the 128 voxels, [132] = x0+128
+__host__ __device__ constexpr int tb_planes(int S) { return 2 * S + 2; }
+__host__ __device__ constexpr size_t tb_smem_bytes(int S, int WP) { return (size_t)tb_planes(S) * (2 * WP + 2) * TB_ROWF * sizeof(float); }
+
+#ifndef MAD_HOST_EMULATION
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else  // the CPU test build copies at issue time
+inline void cp_async16(float* dst, const float* src) { for (int i = 0; i < 4; ++i) dst[i] = src[i]; }
+inline void cp_async4(float* dst, const float* src) { dst[0] = src[0]; }
+inline void cp_async_wait_all() {}
+#endif
+
+// six consecutive values x-1 .. x+4 of a tile row (the thread's four voxels and their x-neighbours)
+__device__ __forceinline__ V6<float> tb_row6(const float* __restrict__ row, int lane)
+{
+  // one 16-byte read per lane (conflict-free); the x-neighbours come from the adjacent lanes by shuffle -- scalar reads at a
+  // stride of four floats would be 4-way bank conflicts -- and from the frozen halo slots at the two warp ends
+  const float* q = row + 4 + 4 * lane;
+  const float4 c = *reinterpret_cast<const float4*>(q);
+  float l = __shfl_up_sync(FULL, c.w, 1), r = __shfl_down_sync(FULL, c.x, 1);
+  if (lane == 0) l = q[-1];
+  if (lane == 31) r = q[4];
+  V6<float> w;
+  w.v[0] = l; w.v[1] = c.x; w.v[2] = c.y; w.v[3] = c.z; w.v[4] = c.w; w.v[5] = r;
+  return w;
+}
+__device__ __forceinline__ V4<float> tb_row4(const float* __restrict__ row, int lane)
+{
+  const float4 c = *reinterpret_cast<const float4*>(row + 4 + 4 * lane);
+  V4<float> w;
+  w.v[0] = c.x; w.v[1] = c.y; w.v[2] = c.z; w.v[3] = c.w;
+  return w;
+}
+
+// neighbourhood of a row being relaxed: plane below (m), its own plane (c), plane above (p); rows y-1 (A), y (B), y+1 (C)
+struct TbNb {
+  V6<float> cA, cB, cC, mB, pB;
+  V4<float> mA, mC, pA, pC;
+};
+__device__ __forceinline__ float offdiag16_tb(const CoefRaw& c, const TbNb& n, int j)
+{
+  float s = coef_at(c, 1, j) * n.cB.v[j + 2] + coef_at(c, 2, j) * n.cB.v[j] + coef_at(c, 3, j) * n.cC.v[j + 1] + coef_at(c, 4, j) * n.cA.v[j + 1];
+  s += coef_at(c, 7, j) * ((n.cC.v[j + 2] - n.cA.v[j + 2]) - (n.cC.v[j] - n.cA.v[j]));
+  s += coef_at(c, 5, j) * n.pB.v[j + 1] + coef_at(c, 6, j) * n.mB.v[j + 1];
+  s += coef_at(c, 8, j) * ((n.pB.v[j + 2] - n.mB.v[j + 2]) - (n.pB.v[j] - n.mB.v[j]));
+  s += coef_at(c, 9, j) * ((n.pC.v[j] - n.mC.v[j]) - (n.pA.v[j] - n.mA.v[j]));
+  return s;
+}
+
+template <int S, int WP, int MINB>
+__global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs_tb(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
+                                                                const float* __restrict__ f, float* __restrict__ out, int zc, int oy, int oz,
+                                                                int pfd, int uzero)
+{
+  constexpr int TY = 2 * WP, NP = tb_planes(S), ROWS = TY + 2;
+  MAD_DYNAMIC_SHARED(float, smem);  // [NP][ROWS][TB_ROWF]
+  const int lane = threadIdx.x, w = threadIdx.y;
+  Pos p;
+  p.lane = lane;
+  p.xt = blockIdx.x * TX + lane * 4;
+  p.xl = p.xt < g.nx ? p.xt : 0;
+  p.jl = g.nx - 1 - p.xt;
+  p.xb = p.xt == 0 || (p.jl >= 0 && p.jl < 4);
+  const int x0 = blockIdx.x * TX;
+  const int y0 = (int)blockIdx.y * TY - oy;              // first image row of the tile (may be negative for a shifted grid)
+  const int ya = y0 + 2 * w;                             // the warp's even row; ny is even, so ya + 1 exists whenever ya does
+  const bool valid = ya >= 0 && ya < g.ny;
+  const int ra = 2 * w + 1, rb = ra + 1;                 // tile rows of ya, ya + 1 (tile row 0 = image row y0 - 1)
+  const int rm_a = ya == 0 ? ra + 1 : ra - 1;            // node mirror at the y ends: row -1 is row 1, row ny is row ny - 2
+  const int rp_b = ya + 1 == g.ny - 1 ? rb - 1 : rb + 1;
+  const int zlo = (int)blockIdx.z * zc - oz;
+  const int z0 = max(zlo, 0), z1 = min(zlo + zc, g.nz);
+  if (z0 >= z1) return;                                  // whole CTA
+  const int zmin_load = max(z0 - 1, g.zlo_phys ? 0 : -1), zmax_load = min(z1, g.zhi_phys ? g.nz - 1 : g.nz);
+  auto slot_of = [&](int pz) { return (pz - (z0 - 1)) % NP; };
+  auto tile_row = [&](int slot, int r) { return smem + ((size_t)slot * ROWS + r) * TB_ROWF; };
+  // one plane of the tile (its rows inside the image, with the x halo) -> shared memory, asynchronously
+  auto load_row = [&](int pz, int slot, int r, int yy) {
+    if (yy < 0 || yy >= g.ny) return;
+    const float* src = u + (long long)pz * g.plane + (long long)yy * g.pitch;
+    float* dst = tile_row(slot, r);
+    if (p.xt < g.nx) cp_async16(dst + 4 + 4 * lane, src + p.xt);
+    if (lane == 0 && x0 > 0) cp_async4(dst + 3, src + x0 - 1);
+    if (lane == 31 && x0 + TX < g.nx) cp_async4(dst + 4 + TX, src + x0 + TX);
+  };
+  auto load_plane = [&](int pz) {
+    const int slot = slot_of(pz);
+    load_row(pz, slot, ra, ya);
+    load_row(pz, slot, rb, ya + 1);
+    if (w == 0) load_row(pz, slot, 0, y0 - 1);
+    if (w == WP - 1) load_row(pz, slot, TY + 1, y0 + TY);
+  };
+  if (uzero) {  // the iterate is identically zero (first sweeps of a leg): nothing is loaded, the ring starts as zeros
+    for (int i = (w * 32 + lane) * 4; i < NP * ROWS * TB_ROWF; i += 32 * WP * 4)
+      *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int pz = zmin_load; pz <= min(z0 + 1, zmax_load); ++pz) load_plane(pz);
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  // L2 prefetch of the first-touch stream (packed rows and f of the plane sweep 0 reaches in pfd steps)
+  const char* pfa = coef_prefetch_base(g, u, f, coef, lane, valid ? ya : 0);
+  const long long pf_stride = lane < 8 ? g.plane * 4ll : (long long)g.ny * (g.pitch >> 2) * COEF_WORDS * 16ll;
+  const long long pf_row = lane < 8 ? g.pitch * 4ll : (long long)(g.pitch >> 2) * COEF_WORDS * 16ll;
+
+  // relax the four voxels of the thread in tile row r (image row y) of plane pc with sweep s
+  auto relax = [&](int s, int pc, int r, int y, int rm, int rp) {
+    const int zm = (pc == 0 && g.zlo_phys) ? pc + 1 : pc - 1, zp = (pc == g.nz - 1 && g.zhi_phys) ? pc - 1 : pc + 1;
+    const CoefRaw c = issue_coef(coef, g, p, y, pc);
+    const int o = pc * (int)g.plane + y * g.pitch + p.xl;
+    const V4<float> fv = finish4<float>(issue4(f, o));
+    const int sm = slot_of(zm), sc = slot_of(pc), sp = slot_of(zp);
+    TbNb n;
+    n.cA = tb_row6(tile_row(sc, rm), lane); n.cB = tb_row6(tile_row(sc, r), lane); n.cC = tb_row6(tile_row(sc, rp), lane);
+    n.mB = tb_row6(tile_row(sm, r), lane); n.pB = tb_row6(tile_row(sp, r), lane);
+    n.mA = tb_row4(tile_row(sm, rm), lane); n.mC = tb_row4(tile_row(sm, rp), lane);
+    n.pA = tb_row4(tile_row(sp, rm), lane); n.pC = tb_row4(tile_row(sp, rp), lane);
+    if (p.xb) {
+      mirror_x(n.cA, p.xt, p.jl); mirror_x(n.cB, p.xt, p.jl); mirror_x(n.cC, p.xt, p.jl);
+      mirror_x(n.mB, p.xt, p.jl); mirror_x(n.pB, p.xt, p.jl);
+    }
+    // even x (slots 0, 2), then odd x (1, 3); the right neighbour's new slot 0 arrives by shuffle (lane 31 keeps the frozen halo)
+    const float n0 = fv.v[0] * coef_inv(c, 0) - offdiag16_tb(c, n, 0);
+    const float n2 = fv.v[2] * coef_inv(c, 2) - offdiag16_tb(c, n, 2);
+    n.cB.v[1] = n0; n.cB.v[3] = n2;
+    {
+      const float rr = __shfl_down_sync(FULL, n0, 1);
+      if (lane < 31) n.cB.v[5] = rr;
+      if (p.xb) mirror_x(n.cB, p.xt, p.jl);
+    }
+    const float n1 = fv.v[1] * coef_inv(c, 1) - offdiag16_tb(c, n, 1);
+    const float n3 = fv.v[3] * coef_inv(c, 3) - offdiag16_tb(c, n, 3);
+    __syncwarp();  // every lane has read its neighbours' old values of this row
+    *reinterpret_cast<float4*>(tile_row(sc, r) + 4 + 4 * lane) = make_float4(n0, n1, n2, n3);
+    if (s == S - 1 && p.xt < g.nx) {
+      const float res[4] = {n0, n1, n2, n3};
+      store4<float>(out, o, p.xt, g.nx, res);
+      store_ghosts<float>(g, pc, y * g.pitch + p.xl, p.xt, res);
+    }
+  };
+
+  const int t_end = z1 - 1 + 2 * (S - 1);
+  for (int t = z0; t <= t_end; ++t) {
+    if (!uzero && t + 2 <= zmax_load) load_plane(t + 2);
+    if (pfd > 0 && valid && pfa && t + pfd < z1) {
+      const char* q = pfa + pf_stride * (t + pfd);
+      if (lane >= 4) { mad_prefetch_l2(q); mad_prefetch_l2(q + pf_row); }
+    }
+    // phase 1: the even rows of every sweep's plane (their y-neighbours are odd rows: previous values)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int pc = t - 2 * s;
+      if (valid && pc >= z0 && pc < z1) relax(s, pc, ra, ya, rm_a, rb);
+    }
+    __syncthreads();
+    // phase 2: the odd rows (their y-neighbours were relaxed in phase 1, by this warp and the next one)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int pc = t - 2 * s;
+      if (valid && pc >= z0 && pc < z1) relax(s, pc, rb, ya + 1, ra, rp_b);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+  }
+}
+
 // r = f - A u from the packed rows (the residual that feeds the restriction INSIDE a Gauss-Seidel V-cycle: it is taken
 // with the same fp16-rounded operator the sweeps relax, so the inner cycle is a consistent multigrid cycle for that
 // operator; the outer defect and the stop test keep the exact rows).  Same marching structure, no phases.

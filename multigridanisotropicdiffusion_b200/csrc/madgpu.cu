@@ -54,6 +54,7 @@ struct Level {
   float* D[6];
   uint4* coef16;      // packed fp16 operator rows for the Gauss-Seidel smoother (mad_fast.cuh), built on first use
   bool coef16_valid;
+  int tb_flip;        // temporal blocking: the next fused pass uses the tile grid shifted by half a tile in y and z (alternates per pass)
   bool coef16_off;    // some diagonal of this level is beyond the range of the packed rows (fast::COEF_DIAG_MAX): exact-row sweeps instead
   std::vector<void*> allocs;
 };
@@ -152,6 +153,7 @@ struct madgpu_ctx {
   };
   std::vector<CycleGraph> graphs;
   long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
+  int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB, default 3; 1 = off)
   int coarse_host;         // MADGPU_COARSE_HOST=1: assemble and invert the coarsest operator on the host (round-1 path; cross-check)
   long long coarse_direct_max;  // coarsest grids of up to this many unknowns get the dense inverse (MADGPU_COARSE_DIRECT_MAX, default 4096)
   int prolong_cell;        // MADGPU_PROLONG_CELL=0: keep the generic streaming prolongation for cell-centred transfers too (A/B hook)
@@ -513,6 +515,38 @@ void op_zero(madgpu_ctx* ctx, Level& L, float* p)
   cudaMemsetAsync(p, 0, (size_t)L.g.plane * L.g.nz * sizeof(float), ctx->stream);
 }
 
+// ---- temporal blocking of the Gauss-Seidel sweeps (fast::k_coef_gs_tb) -----------------------------------------------------
+constexpr int TB_WP = 8;  // warps (row pairs) per CTA: tiles of 128 x 16 voxels
+bool use_tb(const madgpu_ctx* ctx, const Level& L)
+{
+  return ctx->gs_tb > 1 && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && use_fast(ctx, L) && gs_pairs(ctx, L) && L.g.ny >= 8 && L.g.nz >= 8;
+}
+// planes per CTA: ~4 waves of the two resident CTAs per SM; long chunks keep the fill / drain steps of the sweep pipeline (2 per
+// fused sweep) and the frozen z faces rare
+int tb_zc(const Geom& g)
+{
+  const long long cxy = (long long)((g.nx + fast::TX - 1) / fast::TX) * ((g.ny + 2 * TB_WP - 1) / (2 * TB_WP));
+  const long long chunks = std::max(1ll, (148ll * 2 * 4) / std::max(1ll, cxy));
+  int zc = (int)std::max(16ll, (g.nz + chunks - 1) / chunks);
+  zc = (zc + 1) & ~1;
+  return std::min(zc, (g.nz + 1) & ~1);
+}
+// sweeps fused by the next pass when `remaining` sweeps of the leg are left
+int tb_fuse(const madgpu_ctx* ctx, int remaining) { return std::min(remaining >= 3 ? 3 : remaining, ctx->gs_tb); }
+
+template <int S>
+void launch_tb(madgpu_ctx* ctx, Level& L, const Geom& gg, int uz)
+{
+  static bool attr_set = false;  // per instantiation; the attribute is a property of the function
+  const size_t smem = fast::tb_smem_bytes(S, TB_WP);
+  if (!attr_set) { cudaFuncSetAttribute(fast::k_coef_gs_tb<S, TB_WP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  const int zc = tb_zc(L.g);
+  const int oy = L.tb_flip ? TB_WP : 0, oz = L.tb_flip ? zc / 2 : 0;
+  const dim3 grid((L.g.nx + fast::TX - 1) / fast::TX, (L.g.ny + oy + 2 * TB_WP - 1) / (2 * TB_WP), (L.g.nz + oz + zc - 1) / zc);
+  MAD_LAUNCH((fast::k_coef_gs_tb<S, TB_WP, 2>), grid, dim3(32, TB_WP), smem, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, oy, oz, ctx->pf_dist, uz);
+  L.tb_flip ^= 1;
+}
+
 double read_scalar(madgpu_ctx* ctx);
 
 // Packed fp16 operator rows of a level (fast::MODE_COEF), built once per tensor.  False when the level cannot use them: out of
@@ -572,7 +606,12 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
     } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && build_coef16(ctx, L)) {
       // fused sweep fed by pre-evaluated fp16 operator rows (built once per tensor and level)
       Scope s(ctx, cls);
-      if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
+      const int fuse = use_tb(ctx, L) ? tb_fuse(ctx, n_iter - it) : 1;
+      if (fuse > 1) {  // `fuse` sweeps of this leg in one pass (temporal blocking)
+        if (fuse == 3) launch_tb<3>(ctx, L, gg, uz);
+        else launch_tb<2>(ctx, L, gg, uz);
+        it += fuse - 1;
+      } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
         const int zc = fast_zc(L.g, 8);
         MAD_LAUNCH((fast::k_coef_gs2<4, 3>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
@@ -832,7 +871,7 @@ bool vcycle_graphed(madgpu_ctx* ctx, int l, bool zero_guess)
     if ((long long)P.n[0] * P.n[1] * P.n[2] <= ctx->graph_voxels) return false;
   }
   std::vector<const void*> state;
-  for (int k = l; k < ctx->nlevels; ++k) state.push_back(ctx->lv[k].u);
+  for (int k = l; k < ctx->nlevels; ++k) { state.push_back(ctx->lv[k].u); state.push_back((const void*)(uintptr_t)ctx->lv[k].tb_flip); }
   madgpu_ctx::CycleGraph* g = nullptr;
   for (auto& c : ctx->graphs)
     if (c.level == l && c.zero_guess == (int)zero_guess && c.smoother == ctx->p.smoother && c.nu == ctx->p.iterations_per_grid &&
@@ -862,14 +901,16 @@ bool vcycle_graphed(madgpu_ctx* ctx, int l, bool zero_guess)
     if (graph) cudaGraphDestroy(graph);
     // the body ran its pointer swaps on the host while capturing; they come back to the entry state after a whole cycle
     bool same = true;
-    for (int k = l; k < ctx->nlevels; ++k) same = same && ctx->lv[k].u == state[k - l];
+    for (int k = l; k < ctx->nlevels; ++k) same = same && ctx->lv[k].u == state[2 * (k - l)] && (const void*)(uintptr_t)ctx->lv[k].tb_flip == state[2 * (k - l) + 1];
     if (!ok || !same) {
       cudaGetLastError();
       if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
       g->bad = true;
       if (!same) {  // cannot happen with nu pre- and nu post-sweeps; restore and run plainly
-        for (int k = l; k < ctx->nlevels; ++k)
-          if (ctx->lv[k].u != state[k - l]) std::swap(ctx->lv[k].u, ctx->lv[k].tmp);
+        for (int k = l; k < ctx->nlevels; ++k) {
+          if (ctx->lv[k].u != state[2 * (k - l)]) std::swap(ctx->lv[k].u, ctx->lv[k].tmp);
+          ctx->lv[k].tb_flip = (int)(uintptr_t)state[2 * (k - l) + 1];
+        }
       }
       return false;
     }
@@ -1535,6 +1576,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->capturing = false;
     e = getenv("MADGPU_PROLONG_CELL");
     ctx->prolong_cell = e ? atoi(e) : 1;
+    e = getenv("MADGPU_GS_TB");
+    ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 3;
     e = getenv("MADGPU_COARSE_HOST");
     ctx->coarse_host = e ? atoi(e) : 0;
     e = getenv("MADGPU_COARSE_DIRECT_MAX");
@@ -1606,6 +1649,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     L.coef16 = nullptr;
     L.coef16_valid = false;
     L.coef16_off = false;
+    L.tb_flip = 0;
     for (int c = 0; c < 6; ++c) L.D[c] = nullptr;
     for (int c = 0; c < ctx->ncomp; ++c) {
       int rc = dalloc(ctx, L.allocs, &L.D[c], L.elems);
@@ -1905,6 +1949,30 @@ int madgpu_set_profiling(madgpu_ctx* ctx, int32_t on)
   if (!ctx) return MADGPU_EINVAL;
   ctx->profiling = on;
   return 0;
+}
+
+int madgpu_gs_leg_plan(const madgpu_ctx* ctx, int32_t level, int32_t n_iter, int32_t* passes, int32_t capacity)
+{
+  if (!ctx || !passes || level < 0 || level >= ctx->nlevels || n_iter < 0) return MADGPU_EINVAL;
+  const Level& L = ctx->lv[level];
+  int np = 0, flip = L.tb_flip;
+  for (int it = 0; it < n_iter; ) {
+    if (np >= capacity) return MADGPU_EINVAL;
+    int32_t* q = passes + 6 * np++;
+    int32_t tile[3];
+    madgpu_gs_tile(ctx, level, tile);
+    const bool tb_ok = ctx->p.smoother == MADGPU_SMOOTHER_GS && use_tb(ctx, L);
+    const int fuse = tb_ok ? tb_fuse(ctx, n_iter - it) : 1;
+    if (fuse > 1) {
+      const int zc = tb_zc(L.g);
+      q[0] = fuse; q[1] = fast::TX; q[2] = 2 * TB_WP; q[3] = zc; q[4] = flip ? TB_WP : 0; q[5] = flip ? zc / 2 : 0;
+      flip ^= 1;
+    } else {
+      q[0] = 1; q[1] = tile[0]; q[2] = tile[1]; q[3] = tile[2]; q[4] = 0; q[5] = 0;
+    }
+    it += fuse;
+  }
+  return np;
 }
 
 int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])

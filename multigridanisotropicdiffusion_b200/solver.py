@@ -245,6 +245,15 @@ class MadSolver:
         self._check(self._lib.madgpu_gs_tile(self._ctx, int(level), t), "gs_tile")
         return None if t[0] == 0 else (t[0], t[1], t[2])
 
+    def gs_leg_plan(self, level=0, n_iter=1):
+        """The passes the next n_iter Gauss-Seidel sweeps on `level` run as: list of dicts(fused, tile=(tx, ty, tz), shift=(oy, oz));
+        a tile of (0, 0, 0) is one pass per colour over the whole level (madgpu_gs_leg_plan)."""
+        buf = (C.c_int32 * (6 * 64))()
+        n = self._lib.madgpu_gs_leg_plan(self._ctx, int(level), int(n_iter), buf, 64)
+        if n < 0:
+            self._check(n, "gs_leg_plan")
+        return [dict(fused=buf[6 * i], tile=(buf[6 * i + 1], buf[6 * i + 2], buf[6 * i + 3]), shift=(buf[6 * i + 4], buf[6 * i + 5])) for i in range(n)]
+
     def relres_history(self) -> np.ndarray:
         p = self.params
         h = np.full(p.number_of_steps * p.max_cycles, np.nan)

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--nu", type=int, default=2)
     ap.add_argument("--wait", default="memop", choices=["memop", "kernel"], help="peer halo: cuStreamWaitValue32 or the bounded k_halo_wait")
+    ap.add_argument("--tb", type=int, default=1, help="MADGPU_GS_TB: Gauss-Seidel sweeps fused per pass.  1 (no temporal blocking) keeps the slab solve bit-identical "
+                    "to the single-context solve; with > 1 the tile grids of a slab and of the whole volume differ, so the images agree to the solver tolerance")
     ap.add_argument("--drop", default="", help="rank:seq -- from that sequence number on the rank's arrival signals are not sent (needs --wait kernel); every rank must report the time-out")
     a = ap.parse_args()
     import hostlib
@@ -41,6 +43,7 @@ def main():
     os.environ["MADGPU_AGGLOMERATE_VOXELS"] = str(a.agglomerate_voxels)
     os.environ["MADGPU_P2P_WAIT"] = a.wait
     os.environ["MADGPU_P2P_TIMEOUT_MS"] = "400"
+    os.environ["MADGPU_GS_TB"] = str(a.tb)
     if a.drop:
         os.environ["MADGPU_P2P_TEST_DROP_SIGNAL"] = a.drop
     L = hostlib.load()
@@ -108,7 +111,10 @@ def main():
     ref, rst = single["out"], single["stats"]
     err = rel_l2(full, ref)
     print(f"single: cycles {rst['cycles_per_step']}  rel-L2 slabs vs single {err:.3e}", flush=True)
-    ok = err < 1e-10 and stats[0]["cycles_per_step"] == rst["cycles_per_step"] and max(stats[0]["final_relres"]) <= 1e-9
+    if a.tb > 1 and a.smoother == "gs":  # different tile grids: same fixed point, not the same iterates
+        ok = err < 2e-8 and all(abs(x - y) <= 1 for x, y in zip(stats[0]["cycles_per_step"], rst["cycles_per_step"])) and max(stats[0]["final_relres"]) <= 1e-9
+    else:
+        ok = err < 1e-10 and stats[0]["cycles_per_step"] == rst["cycles_per_step"] and max(stats[0]["final_relres"]) <= 1e-9
     ok = ok and all(st["cycles_per_step"] == stats[0]["cycles_per_step"] for st in stats) and L.mad_host_live_allocs() == 0
     print("SLAB_EMULATION_OK" if ok else "SLAB_EMULATION_FAILED", flush=True)
     return 0 if ok else 1

@@ -40,6 +40,14 @@ def test_eight_ranks_peer_halo():
     assert "'planes_per_rank': [8, 4, 2]" in out
 
 
+def test_temporal_blocking_on_slabs():
+    """Fused Gauss-Seidel sweeps (k_coef_gs_tb) on z-slabs: the frozen halo of a pass includes the ghost planes, the last fused sweep
+    stores the slab's boundary planes into the neighbours' ghost planes.  The tile grid of a slab differs from the whole volume's,
+    so the comparison is on the converged image and the cycle counts."""
+    _run("--world", "2", "--peer", "1", "--shape", "32,24,24", "--nu", "3", "--tb", "3")
+    _run("--world", "4", "--peer", "0", "--agglomerate-voxels", "1000", "--nu", "3", "--tb", "3")
+
+
 def test_fmg_on_slabs_with_a_multi_level_agglomerated_hierarchy():
     """agglomerated_fmg: the FMG recursion below the agglomeration level runs as the sub-context's own FullMultiGrid on rank 0."""
     out = _run("--world", "2", "--peer", "1", "--cycle", "fmg", "--shape", "32,24,24")

@@ -141,6 +141,8 @@ GS_CASES = [
     ((23, 25, 27), (0.3125, 0.3125, 0.5), 0.1),
     ((9, 6, 131), (1.0, 0.7, 1.3), 0.1),
     ((14, 18, 200), (1.0, 1.0, 1.0), 0.1),        # even ny > 8: several row-pair tiles
+    ((40, 36, 136), (0.3125, 0.3125, 0.5), 0.1),  # temporal blocking: several 16-row tiles, two z chunks on the shifted grid, two warp columns
+    ((19, 16, 64), (1.0, 1.0, 1.0), 0.1),         # odd plane count, exactly one tile of rows
 ]
 
 
@@ -158,9 +160,11 @@ def gs_env(request, monkeypatch):
 
 @pytest.mark.parametrize("case", GS_CASES)
 def test_fused_gs_sweep_is_the_documented_ordering(case, gs_env):
-    """One fused sweep == sequential Gauss-Seidel in the documented order (z planes; even rows: even x, odd x;
-    odd rows), tile-local, evaluated on the CPU with the oracle's explicit operator rows."""
-    from util import gs_tile_sweep
+    """A Gauss-Seidel leg == the documented ordering, evaluated on the CPU with the oracle's explicit operator rows: passes as
+    planned by the library (gs_leg_plan); inside a tile sequential Gauss-Seidel (z planes; even rows: even x, odd x; odd rows);
+    a pass that fuses several sweeps (temporal blocking, packed rows only) keeps the values outside the tile frozen at those it
+    started from and alternates the tile grid between passes."""
+    from util import gs_leg_model
     s, o = _mk(case, smoother=0)
     tile = s.gs_tile(0)
     assert tile is not None and tile[0] == 128
@@ -170,13 +174,17 @@ def test_fused_gs_sweep_is_the_documented_ordering(case, gs_env):
     # exact rows: fp32 rounding only; packed fp16 rows: the operator itself is rounded to 11 bits (the smoother inside
     # an exact defect-correction loop, see k_coef_gs)
     tol = 2e-6 if gs_env[1] == 0 else 2e-3
-    g1 = s.op_smooth(0, u, f, smoother=0, n_iter=1)
-    r1 = gs_tile_sweep(S, u.astype(np.float64), f.astype(np.float64), tile)
-    assert rel_l2(g1, r1) < tol, rel_l2(g1, r1)
-    assert np.abs(g1 - r1).max() < 15 * tol * np.abs(r1).max()
-    g2 = s.op_smooth(0, u, f, smoother=0, n_iter=2)
-    r2 = gs_tile_sweep(S, r1, f.astype(np.float64), tile)
-    assert rel_l2(g2, r2) < 2 * tol, rel_l2(g2, r2)
+    fused_seen = 0
+    for n_iter in (1, 2, 3, 5):
+        plan = s.gs_leg_plan(0, n_iter)  # before the call: the plan depends on the alternation state the call advances
+        assert sum(p["fused"] for p in plan) == n_iter
+        fused_seen = max(fused_seen, max(p["fused"] for p in plan))
+        g = s.op_smooth(0, u, f, smoother=0, n_iter=n_iter)
+        r = gs_leg_model(S, u.astype(np.float64), f.astype(np.float64), plan)
+        assert rel_l2(g, r) < n_iter * tol, (n_iter, plan, rel_l2(g, r))
+        assert np.abs(g - r).max() < 15 * n_iter * tol * np.abs(r).max()
+    if gs_env[1] == 1 and gs_env[2] == 1 and shape[1] % 2 == 0 and shape[1] >= 8 and shape[0] >= 8:
+        assert fused_seen == 3  # the default configuration really fuses
     s.close()
 
 

@@ -72,7 +72,17 @@ def load_ved_test():
     return z["image"], tuple(float(s) for s in z["spacing"])
 
 
-def gs_tile_sweep(S, u, f, tile, outside=None):
+def gs_leg_model(S, u, f, plan):
+    """CPU model of a Gauss-Seidel leg as the library plans it (MadSolver.gs_leg_plan): every pass runs `fused` sweeps of
+    gs_tile_sweep on its (possibly shifted) tile grid with the values outside a tile frozen at those the pass started from."""
+    for p in plan:
+        start = u
+        for _ in range(p["fused"]):
+            u = gs_tile_sweep(S, u, f, p["tile"], outside=start, shift=p["shift"])
+    return u
+
+
+def gs_tile_sweep(S, u, f, tile, outside=None, shift=(0, 0)):
     """CPU model (numpy, explicit operator rows `S` from the oracle) of the fused GPU Gauss-Seidel sweep:
     tiles of (tx, ty, tz) voxels; inside a tile planes in z order, each plane as even rows (even x, odd x)
     then odd rows; values outside the tile are those of `outside` (default: `u`, the previous sweep; the kernel
@@ -86,8 +96,8 @@ def gs_tile_sweep(S, u, f, tile, outside=None):
     w = np.zeros((nz + 2, ny + 2, nx + 2))
     w[1:-1, 1:-1, 1:-1] = u
     tx = np.arange(-1, nx + 1) // TX
-    ty = np.arange(-1, ny + 1) // TY
-    tz = np.arange(-1, nz + 1) // TZ
+    ty = (np.arange(-1, ny + 1) + shift[0]) // TY  # shift: the tile grid starts at (-shift y, -shift z)
+    tz = (np.arange(-1, nz + 1) + shift[1]) // TZ
     for z in range(nz):
         for (cy, cx) in ((0, 0), (0, 1), (1, 0), (1, 1)):
             ys = np.arange(cy, ny, 2)
