@@ -16,6 +16,7 @@
 #include "../../include/madgpu.h"
 #include "mad_kernels.cuh"
 #include "mad_fast.cuh"
+#include "mad_fast2d.cuh"
 
 // Every kernel launch of this file goes through MAD_LAUNCH((kernel<...>), grid, block, shared bytes, stream, args...) -- the kernel
 // name in parentheses so that template commas survive the preprocessor.  Here it is the plain <<<>>> launch; the CPU test build
@@ -141,6 +142,7 @@ struct madgpu_ctx {
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
   int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 -- the row the fp32 sweeps relax -- and applied in fp64 (default; MADGPU_RES64_COEF32=0: fp64 row)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
+  int fast2d;       // MADGPU_FAST2D=0: 2-D levels keep the generic one-pixel-per-thread kernels (A/B and cross-check hook)
   // CUDA graphs of the launch-bound part of a V-cycle: vcycle(l) for the first level of at most graph_voxels voxels (and with it
   // everything below) is captured once per (level, zero guess, solver settings, ping-pong state) and replayed
   struct CycleGraph {
@@ -153,7 +155,9 @@ struct madgpu_ctx {
   };
   std::vector<CycleGraph> graphs;
   long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
-  int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB, default 3; 1 = off)
+  int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB = 2 or 3; default 1 = off:
+                           // measured on B200 at 512^3 a fused pass of 3 sweeps takes 2.04 ms against 3 x 0.77 ms -- the packed rows of the older planes
+                           // come from L2, not HBM, but still cross the L2 -> SM fabric once per sweep -- and its frozen tile faces cost 3 V-cycles in 6)
   int coarse_host;         // MADGPU_COARSE_HOST=1: assemble and invert the coarsest operator on the host (round-1 path; cross-check)
   long long coarse_direct_max;  // coarsest grids of up to this many unknowns get the dense inverse (MADGPU_COARSE_DIRECT_MAX, default 4096)
   int prolong_cell;        // MADGPU_PROLONG_CELL=0: keep the generic streaming prolongation for cell-centred transfers too (A/B hook)
@@ -217,6 +221,30 @@ int fast_zc(const Geom& g, int wy)
   return std::min(zc, std::max(g.nz, 1));
 }
 dim3 fast_grid(const Geom& g, int wy, int zc) { return dim3((g.nx + fast::TX - 1) / fast::TX, (g.ny + wy - 1) / wy, (g.nz + zc - 1) / zc); }
+
+// ---- 2-D streaming kernels (mad_fast2d.cuh): one warp per strip of 128 columns and chunk of yc rows ----------------------------
+bool use_fast2(const madgpu_ctx* ctx, const Level& L)
+{
+  return ctx->dim == 2 && ctx->fast2d && L.g.nx >= ctx->fast_min_nx && L.g.ny >= 4 && L.elems < (1ull << 31);
+}
+constexpr int F2_WY = 4;  // warps per CTA (independent of each other)
+// rows per warp: enough warps for ~8 per SM sub-partition on large images, at least 8 rows so that the two start-up rows stay cheap
+int fast2_yc(const Geom& g)
+{
+  const long long strips = (g.nx + fast::TX - 1) / fast::TX;
+  const long long chunks = std::max(1ll, (148ll * 32) / std::max(1ll, strips));
+  const int yc = (int)std::max(8ll, (g.ny + chunks - 1) / chunks);
+  return std::min(yc, std::max(g.ny, 1));
+}
+template <int MODE, typename T, typename UT, typename FT>
+size_t launch_fast2(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, float* out, double* partials, float omega, int uzero = 0)
+{
+  const int yc = fast2_yc(L.g);
+  const int chunks = (L.g.ny + yc - 1) / yc;
+  const dim3 fg((L.g.nx + fast::TX - 1) / fast::TX, (chunks + F2_WY - 1) / F2_WY);
+  MAD_LAUNCH((fast::k2_sweep<MODE, T, UT, FT, F2_WY>), fg, dim3(32, F2_WY), 0, ctx->stream, L.g, tensor_of(L), u, f, out, partials, omega, yc, uzero);
+  return (size_t)fg.x * fg.y;
+}
 
 // One streaming pass (MODE_WJ / MODE_RES) over a level; returns the number of CTAs (= partial sums written).
 // ctx->fast_cfg selects the CTA shape / register cap (tuning hook MADGPU_FAST_CFG).
@@ -589,7 +617,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   const int cls = l == 0 ? MADGPU_K_SMOOTH0 : MADGPU_K_SMOOTHC;
   const Tensor D = tensor_of(L);
-  const bool streaming = use_fast(ctx, L) && (smoother == MADGPU_SMOOTHER_WJ || ctx->gs_fused);
+  const bool streaming = (use_fast(ctx, L) && (smoother == MADGPU_SMOOTHER_WJ || ctx->gs_fused)) || use_fast2(ctx, L);
   if (zero_first && (!streaming || n_iter == 0)) { op_zero(ctx, L, L.u); zero_first = false; }
   for (int it = 0; it < n_iter; ++it) {
     const int uz = zero_first && it == 0;
@@ -599,9 +627,15 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
     if (smoother == MADGPU_SMOOTHER_WJ) {
       Scope s(ctx, cls);
       if (use_fast(ctx, L)) launch_fast<fast::MODE_WJ, float, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega, uz);
+      else if (use_fast2(ctx, L)) launch_fast2<fast::M2_WJ, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, (float)ctx->p.omega, uz);
       else if (ctx->dim == 3) MAD_LAUNCH((k_jacobi<3>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       else MAD_LAUNCH((k_jacobi<2>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       if (!use_fast(ctx, L)) halo_dirty(ctx, L.tmp);
+      std::swap(L.u, L.tmp);
+    } else if (use_fast2(ctx, L)) {
+      // 2-D: one pass, rows in y order, even then odd columns, exact inside a tile of 128 columns x yc rows (mad_fast2d.cuh)
+      Scope s(ctx, cls);
+      launch_fast2<fast::M2_GS, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, 0.f, uz);
       std::swap(L.u, L.tmp);
     } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && build_coef16(ctx, L)) {
       // fused sweep fed by pre-evaluated fp16 operator rows (built once per tensor and level)
@@ -706,6 +740,11 @@ void op_residual32(madgpu_ctx* ctx, int l, float* out, bool norm)
     if (norm) reduce_partials(ctx, nb);
     return;
   }
+  if (use_fast2(ctx, L)) {
+    const size_t nb = launch_fast2<fast::M2_RES, float, float, float>(ctx, L, L.u, L.f, out, part, 0.f);
+    if (norm) reduce_partials(ctx, nb);
+    return;
+  }
   if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, float, float, float, float>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, out, part);
   else MAD_LAUNCH((k_residual<2, float, float, float, float>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, out, part);
   halo_dirty(ctx, out);
@@ -727,6 +766,9 @@ void op_residual64(madgpu_ctx* ctx, float* r32_or_null, double* r64_or_null)
     const size_t nb = ctx->res64_c32 ? launch_fast<fast::MODE_RES_C32, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f)
                                      : launch_fast<fast::MODE_RES, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f);
     reduce_partials(ctx, nb);
+    return;
+  } else if (use_fast2(ctx, L)) {
+    reduce_partials(ctx, launch_fast2<fast::M2_RES, double, double, double>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f));
     return;
   } else {
     if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, double, double, double, float>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r32_or_null, ctx->partials);
@@ -756,6 +798,12 @@ void op_restrict(madgpu_ctx* ctx, int lf, const TI* fine, float* coarse, int cls
       constexpr int WY = 8;
       const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (C.g.ny + WY - 1) / WY, C.g.nz);
       MAD_LAUNCH((fast::k_fast_restrict<WY>), fg, dim3(32, WY), 0, ctx->stream, F.g, C.g, transfer_of(C), fine, coarse);
+      return;
+    }
+    if (use_fast2(ctx, F)) {
+      constexpr int WY = 4;
+      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (C.g.ny + WY - 1) / WY);
+      MAD_LAUNCH((fast::k2_restrict<WY>), fg, dim3(32, WY), 0, ctx->stream, F.g, C.g, transfer_of(C), fine, coarse);
       return;
     }
   }
@@ -789,6 +837,12 @@ void op_prolong(madgpu_ctx* ctx, int lf, const float* coarse, TO* fine)
       const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY, (F.g.nz + fast::PROLONG_ZB - 1) / fast::PROLONG_ZB);
       MAD_LAUNCH((fast::k_fast_prolong<ADD, WY>), fg, dim3(32, WY), 0, ctx->stream, C.g, gg, transfer_of(C), coarse, fine);
       halo_signal(ctx, fine);
+      return;
+    }
+    if (use_fast2(ctx, F)) {
+      constexpr int WY = 4;
+      const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (F.g.ny + WY - 1) / WY);
+      MAD_LAUNCH((fast::k2_prolong<ADD, WY>), fg, dim3(32, WY), 0, ctx->stream, C.g, F.g, transfer_of(C), coarse, fine);
       return;
     }
   }
@@ -1172,6 +1226,22 @@ int invert_dense(std::vector<double>& A, int n, std::vector<double>& inv)
   return 0;
 }
 
+// MADGPU_SETUP_TRACE=1: where the time of a tensor set-up goes (stream-synchronised wall clock per phase, on stderr)
+struct SetupTrace {
+  madgpu_ctx* ctx;
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  explicit SetupTrace(madgpu_ctx* c) : ctx(c), on(getenv("MADGPU_SETUP_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what)
+  {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[madgpu set-up] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 // Direct solver of the coarsest grid (mad/itkDirectSolver.hxx:32-88): the operator is assembled and inverted ON THE DEVICE
 // (Gauss-Jordan with partial pivoting in fp64 on [A | I]); the inverse is applied as a GEMV per coarse solve.  host = true keeps
 // the round-1 path (assembly + LU on the host), which the tests compare with.
@@ -1256,11 +1326,14 @@ int build_coarse_solver(madgpu_ctx* ctx)
 int finish_tensor(madgpu_ctx* ctx)
 {
   for (int l = 0; l < ctx->nlevels; ++l) { ctx->lv[l].coef16_valid = false; ctx->lv[l].coef16_off = false; }
+  SetupTrace tr(ctx);
   drop_graphs(ctx);  // the captured cycles read the packed rows of the previous tensor
+  tr.mark("drop graphs");
   for (int l = 0; l + 1 < ctx->nlevels; ++l)
     for (int c = 0; c < ctx->ncomp; ++c)  // mad/itkGridsHierarchy.hxx:149-162
       op_restrict<float>(ctx, l, ctx->lv[l].D[c], ctx->lv[l + 1].D[c], MADGPU_K_MISC);
   CU(cudaGetLastError());
+  tr.mark("tensor restriction");
   if (ctx->world > 1) {
     // tensor of the agglomeration level -> rank 0, which finishes the hierarchy below it
     Level& A = ctx->lv[ctx->nlevels - 1];
@@ -1284,6 +1357,7 @@ int finish_tensor(madgpu_ctx* ctx)
     return 0;
   }
   const int rc = build_coarse_solver(ctx);
+  tr.mark("coarsest-grid inverse");
   if (rc != 0) return rc;
   ctx->tensor_set = true;
   return 0;
@@ -1317,6 +1391,8 @@ int set_tensor_host(madgpu_ctx* ctx, const T* aos)
     stage[i] = (T*)ctx->stage[i];
     CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
   }
+  SetupTrace tr(ctx);
+  tr.mark("staging buffers");
   int k = 0;
   for (long long first = 0; first < nvox; first += chunk, k ^= 1) {
     const long long cnt = std::min(chunk, nvox - first);
@@ -1329,6 +1405,7 @@ int set_tensor_host(madgpu_ctx* ctx, const T* aos)
     CU(cudaEventRecord(done[k], ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  tr.mark("upload + ingest");
   for (int i = 0; i < 2; ++i) cudaEventDestroy(done[i]);
   const int rc = finish_tensor(ctx);
   ctx->st.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1553,6 +1630,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
   {
     const char* e = getenv("MADGPU_FAST_MIN_NX");  // test hook: 0 forces the streaming kernels on every 3-D level
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
+    e = getenv("MADGPU_FAST2D");
+    ctx->fast2d = e ? atoi(e) : 1;
     e = getenv("MADGPU_PF_DIST");
     ctx->pf_dist = e ? atoi(e) : 2;
     e = getenv("MADGPU_GS_PAIRS");
@@ -1577,7 +1656,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     e = getenv("MADGPU_PROLONG_CELL");
     ctx->prolong_cell = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_TB");
-    ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 3;
+    ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 1;
     e = getenv("MADGPU_COARSE_HOST");
     ctx->coarse_host = e ? atoi(e) : 0;
     e = getenv("MADGPU_COARSE_DIRECT_MAX");
@@ -1982,6 +2061,8 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
     const int wy = (ctx->gs_coef16 && !L.coef16_off) ? (gs_pairs(ctx, L) ? 8 : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
     tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
+  } else if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast2(ctx, L)) {
+    tile[0] = fast::TX; tile[1] = fast2_yc(L.g); tile[2] = 1;  // 2-D ordering: rows in y order, even then odd columns (mad_fast2d.cuh)
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level
   }

@@ -14,7 +14,7 @@ FAKE_NCCL = os.path.join(OUT, "libfakenccl.so")
 def build():
     csrc = os.path.join(ROOT, "multigridanisotropicdiffusion_b200", "csrc")
     deps = [os.path.join(HERE, f) for f in ("madgpu_host.cpp", "fiber_shim.h", "fake_nccl.cpp", "build.sh")]
-    deps += [os.path.join(csrc, f) for f in ("madgpu.cu", "mad_kernels.cuh", "mad_fast.cuh", "ved.cu", "ved_kernels.cuh", "ved_math.h")]
+    deps += [os.path.join(csrc, f) for f in ("madgpu.cu", "mad_kernels.cuh", "mad_fast.cuh", "mad_fast2d.cuh", "ved.cu", "ved_kernels.cuh", "ved_math.h")]
     deps += [os.path.join(ROOT, "tests", "fake_cuda", f) for f in ("cuda_runtime.h", "cuda_fp16.h")]
     deps += [os.path.join(ROOT, "include", "madgpu.h"), os.path.join(ROOT, "include", "madved.h")]
     newest = max(os.path.getmtime(d) for d in deps)

@@ -146,11 +146,12 @@ GS_CASES = [
 ]
 
 
-@pytest.fixture(params=[(0, 0, 0), (1, 0, 0), (7, 0, 0), (8, 0, 0), (0, 1, 0), (0, 1, 1)],
-                ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}{'-pairs' if c[2] else ''}")
+@pytest.fixture(params=[(0, 0, 0, 1), (1, 0, 0, 1), (7, 0, 0, 1), (8, 0, 0, 1), (0, 1, 0, 1), (0, 1, 1, 1), (0, 1, 1, 3)],
+                ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}{'-pairs' if c[2] else ''}{'-tb3' if c[3] == 3 else ''}")
 def gs_env(request, monkeypatch):
-    """(kernel variant, packed fp16 operator rows, one warp per row pair): the default is (0, 1, 1); the exact-row
-    variants pin the ordering to fp32 rounding."""
+    """(kernel variant, packed fp16 operator rows, one warp per row pair, sweeps fused per pass): the default is (0, 1, 1, 1); the
+    exact-row variants pin the ordering to fp32 rounding; the last one is the opt-in temporal blocking (MADGPU_GS_TB=3)."""
+    monkeypatch.setenv("MADGPU_GS_TB", str(request.param[3]))
     monkeypatch.setenv("MADGPU_FAST_MIN_NX", "0")
     monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param[0]))
     monkeypatch.setenv("MADGPU_GS_COEF16", str(request.param[1]))
@@ -183,8 +184,10 @@ def test_fused_gs_sweep_is_the_documented_ordering(case, gs_env):
         r = gs_leg_model(S, u.astype(np.float64), f.astype(np.float64), plan)
         assert rel_l2(g, r) < n_iter * tol, (n_iter, plan, rel_l2(g, r))
         assert np.abs(g - r).max() < 15 * n_iter * tol * np.abs(r).max()
-    if gs_env[1] == 1 and gs_env[2] == 1 and shape[1] % 2 == 0 and shape[1] >= 8 and shape[0] >= 8:
-        assert fused_seen == 3  # the default configuration really fuses
+    if gs_env[3] == 3 and shape[1] % 2 == 0 and shape[1] >= 8 and shape[0] >= 8:
+        assert fused_seen == 3  # MADGPU_GS_TB=3 really fuses
+    if gs_env[3] == 1:
+        assert fused_seen == 1
     s.close()
 
 
