@@ -1456,5 +1456,64 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict(Geom gf, Geom gc, Tra
   else if (xc0 < gc.nx) coarse[o] = a0;
 }
 
+// The same operator for transfers that are cell-centred along all three axes (every level of a power-of-two volume), marching
+// along z: a warp owns a coarse row, a thread its coarse voxels 2t, 2t+1; every fine plane is reduced ONCE to its xy-restricted
+// row (four fine rows, one 16-byte load + two shuffles each) and enters the two coarse planes it contributes to from registers
+// -- two fine planes loaded per coarse plane instead of the four k_fast_restrict re-reads through L1 / L2.
+// grid = (ceil(nxf/128), ceil(nyc/WY), ceil(nzc/zcc)), block = (32, WY); needs nxf, nyf, nzf even.
+template <int WY>
+__global__ void __launch_bounds__(32 * WY) k_fast_restrict_cell(Geom gf, Geom gc, const float* __restrict__ fine, float* __restrict__ coarse, int zcc)
+{
+  Pos p;
+  p.lane = threadIdx.x;
+  p.xt = blockIdx.x * TX + p.lane * 4;
+  p.xl = p.xt < gf.nx ? p.xt : 0;
+  p.edge = p.lane == 0 || p.lane == 31;
+  p.dh = (p.lane == 0 ? max(p.xt - 1, 0) : min(p.xt + 4, gf.nx - 1)) - p.xl;
+  const int yc = blockIdx.y * WY + threadIdx.y;
+  if (yc >= gc.ny) return;  // whole warp
+  const int k0 = blockIdx.z * zcc, k1 = min(k0 + zcc, gc.nz);
+  float wy[4], wxa[4], wxb[4];
+  restrict_taps(yc, gc.ny, 1, wy);
+  const int xc0 = p.xt >> 1;  // coarse voxels xc0, xc0 + 1
+  restrict_taps(min(xc0, gc.nx - 1), gc.nx, 1, wxa);
+  restrict_taps(min(xc0 + 1, gc.nx - 1), gc.nx, 1, wxb);
+  int ro[4];  // the four contributing fine rows (clamped rows carry weight 0)
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) ro[ky] = min(max(2 * yc + ky - 1, 0), gf.ny - 1) * gf.pitch + p.xl;
+  const int zlo = gf.zlo_phys ? 0 : -1, zhi = gf.zhi_phys ? gf.nz - 1 : gf.nz;  // ghost planes of a z-slab are valid
+  struct P2 { float a, b; };
+  // xy-restricted row of fine plane z (clamped into the valid planes; a clamped plane only ever meets weight 0)
+  auto plane = [&](int z) {
+    const int zb = min(max(z, zlo), zhi) * (int)gf.plane;
+    Raw6<float> rw[4];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) rw[ky] = issue6(fine, zb + ro[ky], p);
+    P2 o = {0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const V6<float> v = finish6<float, float>(rw[ky], p);
+      float m[6];  // voxels beyond the fine row only ever meet zero weights, but may hold anything: mask them
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const int fx = p.xt - 1 + i; m[i] = (fx >= 0 && fx < gf.nx) ? v.v[i] : 0.f; }
+      o.a += wy[ky] * (wxa[0] * m[0] + wxa[1] * m[1] + wxa[2] * m[2] + wxa[3] * m[3]);
+      o.b += wy[ky] * (wxb[0] * m[2] + wxb[1] * m[3] + wxb[2] * m[4] + wxb[3] * m[5]);
+    }
+    return o;
+  };
+  P2 pm = plane(2 * k0 - 1), p0 = plane(2 * k0);
+  for (int k = k0; k < k1; ++k) {
+    const P2 p1 = plane(2 * k + 1), p2 = plane(2 * k + 2);
+    float wz[4];
+    restrict_taps(k, gc.nz, 1, wz, gc.zlo_phys != 0, gc.zhi_phys != 0);
+    const float b0 = wz[0] * pm.a + wz[1] * p0.a + wz[2] * p1.a + wz[3] * p2.a;
+    const float b1 = wz[0] * pm.b + wz[1] * p0.b + wz[2] * p1.b + wz[3] * p2.b;
+    const long long oo = (long long)k * gc.plane + (long long)yc * gc.pitch + xc0;
+    if (xc0 + 1 < gc.nx) *reinterpret_cast<float2*>(coarse + oo) = make_float2(b0, b1);
+    else if (xc0 < gc.nx) coarse[oo] = b0;
+    pm = p1; p0 = p2;
+  }
+}
+
 }  // namespace fast
 }  // namespace mad

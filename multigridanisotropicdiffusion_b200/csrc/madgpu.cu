@@ -161,6 +161,7 @@ struct madgpu_ctx {
   int coarse_host;         // MADGPU_COARSE_HOST=1: assemble and invert the coarsest operator on the host (round-1 path; cross-check)
   long long coarse_direct_max;  // coarsest grids of up to this many unknowns get the dense inverse (MADGPU_COARSE_DIRECT_MAX, default 4096)
   int prolong_cell;        // MADGPU_PROLONG_CELL=0: keep the generic streaming prolongation for cell-centred transfers too (A/B hook)
+  int restrict_cell;       // MADGPU_RESTRICT_CELL=0: likewise for the restriction
   bool capturing;
 };
 
@@ -796,6 +797,14 @@ void op_restrict(madgpu_ctx* ctx, int lf, const TI* fine, float* coarse, int cls
   if constexpr (std::is_same<TI, float>::value) {
     if (use_fast(ctx, F) && F.g.nx >= 8) {
       constexpr int WY = 8;
+      if (C.cent[0] == 1 && C.cent[1] == 1 && C.cent[2] == 1 && ctx->restrict_cell) {
+        // cell-centred along all axes (power-of-two volumes): the marching kernel, every fine plane reduced once
+        const int gx = (F.g.nx + fast::TX - 1) / fast::TX, gy = (C.g.ny + WY - 1) / WY;
+        const int chunks = std::max(1, std::min(C.g.nz, (148 * 8 + gx * gy - 1) / (gx * gy)));
+        const int zcc = (C.g.nz + chunks - 1) / chunks;
+        MAD_LAUNCH((fast::k_fast_restrict_cell<WY>), dim3(gx, gy, (C.g.nz + zcc - 1) / zcc), dim3(32, WY), 0, ctx->stream, F.g, C.g, fine, coarse, zcc);
+        return;
+      }
       const dim3 fg((F.g.nx + fast::TX - 1) / fast::TX, (C.g.ny + WY - 1) / WY, C.g.nz);
       MAD_LAUNCH((fast::k_fast_restrict<WY>), fg, dim3(32, WY), 0, ctx->stream, F.g, C.g, transfer_of(C), fine, coarse);
       return;
@@ -1655,6 +1664,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->capturing = false;
     e = getenv("MADGPU_PROLONG_CELL");
     ctx->prolong_cell = e ? atoi(e) : 1;
+    e = getenv("MADGPU_RESTRICT_CELL");
+    ctx->restrict_cell = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_TB");
     ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 1;
     e = getenv("MADGPU_COARSE_HOST");
