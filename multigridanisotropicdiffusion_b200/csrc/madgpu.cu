@@ -93,6 +93,10 @@ struct madgpu_ctx {
   double *u64, *f64;  // level-0 outer fields (plane-0 pointers)
   std::vector<void*> allocs;
   double* Ainv;  // device, ncoarse^2
+  double* gjM;   // device work matrix [A | I] of the Gauss-Jordan inverse (+ saved column, singular flag), kept between tensors
+  int gj_n;
+  cudaGraphExec_t gj_exec;  // the inverse's launches, captured once
+  bool gj_graph_bad;
   int ncoarse;
   bool coarse_direct;
   double* partials;
@@ -140,9 +144,11 @@ struct madgpu_ctx {
   int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
+  int res64_minb;   // MADGPU_RES64_MINB=3: register cap of the fp64 residual for 3 CTAs per SM
   int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 -- the row the fp32 sweeps relax -- and applied in fp64 (default; MADGPU_RES64_COEF32=0: fp64 row)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
   int fast2d;       // MADGPU_FAST2D=0: 2-D levels keep the generic one-pixel-per-thread kernels (A/B and cross-check hook)
+  long long fast2d_min_pixels;  // MADGPU_FAST2D_MIN_PIXELS (default 2^20): see use_fast2
   // CUDA graphs of the launch-bound part of a V-cycle: vcycle(l) for the first level of at most graph_voxels voxels (and with it
   // everything below) is captured once per (level, zero guess, solver settings, ping-pong state) and replayed
   struct CycleGraph {
@@ -224,9 +230,17 @@ int fast_zc(const Geom& g, int wy)
 dim3 fast_grid(const Geom& g, int wy, int zc) { return dim3((g.nx + fast::TX - 1) / fast::TX, (g.ny + wy - 1) / wy, (g.nz + zc - 1) / zc); }
 
 // ---- 2-D streaming kernels (mad_fast2d.cuh): one warp per strip of 128 columns and chunk of yc rows ----------------------------
-bool use_fast2(const madgpu_ctx* ctx, const Level& L)
+// Gauss-Seidel: at every size (one launch per sweep instead of four colour passes).  Weighted Jacobi, residuals and transfers: only
+// on levels of at least fast2d_min_pixels pixels -- a warp marches its rows one after the other, so a small level (512^2: 256
+// warps) is latency-bound where the one-pixel-per-thread kernels spread it over the whole GPU (measured on B200, 512^2: a weighted-
+// Jacobi V(3,3) cycle 0.34 ms with the streaming kernels everywhere against 0.21 ms; 8192^2: 4.8 ms against 10.1 ms).
+bool use_fast2_gs(const madgpu_ctx* ctx, const Level& L)
 {
   return ctx->dim == 2 && ctx->fast2d && L.g.nx >= ctx->fast_min_nx && L.g.ny >= 4 && L.elems < (1ull << 31);
+}
+bool use_fast2(const madgpu_ctx* ctx, const Level& L)
+{
+  return use_fast2_gs(ctx, L) && (long long)L.g.nx * L.g.ny >= ctx->fast2d_min_pixels;
 }
 constexpr int F2_WY = 4;  // warps per CTA (independent of each other)
 // rows per warp: enough warps for ~8 per SM sub-partition on large images, at least 8 rows so that the two start-up rows stay cheap
@@ -265,6 +279,7 @@ size_t launch_fast(madgpu_ctx* ctx, const Level& L, const UT* u, const FT* f, OT
   } while (0)
   if (sizeof(T) == 8) {
     if (ctx->fast_cfg == 4) MAD_FAST_LAUNCH(4, 2, true);
+    if (ctx->res64_minb == 3) MAD_FAST_LAUNCH(4, 3, false);  // 168 registers (spills) for 12 instead of 8 warps per SM: A/B hook MADGPU_RES64_MINB
     MAD_FAST_LAUNCH(4, 2, false);
   }
   switch (ctx->fast_cfg) {
@@ -618,7 +633,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   const int cls = l == 0 ? MADGPU_K_SMOOTH0 : MADGPU_K_SMOOTHC;
   const Tensor D = tensor_of(L);
-  const bool streaming = (use_fast(ctx, L) && (smoother == MADGPU_SMOOTHER_WJ || ctx->gs_fused)) || use_fast2(ctx, L);
+  const bool streaming = (use_fast(ctx, L) && (smoother == MADGPU_SMOOTHER_WJ || ctx->gs_fused)) || (smoother == MADGPU_SMOOTHER_WJ ? use_fast2(ctx, L) : use_fast2_gs(ctx, L));
   if (zero_first && (!streaming || n_iter == 0)) { op_zero(ctx, L, L.u); zero_first = false; }
   for (int it = 0; it < n_iter; ++it) {
     const int uz = zero_first && it == 0;
@@ -633,7 +648,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       else MAD_LAUNCH((k_jacobi<2>), g, b, 0, ctx->stream, L.g, D, L.u, L.f, L.tmp, (float)ctx->p.omega);
       if (!use_fast(ctx, L)) halo_dirty(ctx, L.tmp);
       std::swap(L.u, L.tmp);
-    } else if (use_fast2(ctx, L)) {
+    } else if (use_fast2_gs(ctx, L)) {
       // 2-D: one pass, rows in y order, even then odd columns, exact inside a tile of 128 columns x yc rows (mad_fast2d.cuh)
       Scope s(ctx, cls);
       launch_fast2<fast::M2_GS, float, float, float>(ctx, L, L.u, L.f, L.tmp, nullptr, 0.f, uz);
@@ -1267,26 +1282,55 @@ int build_coarse_solver(madgpu_ctx* ctx)
   if (ctx->Ainv && ctx->ncoarse != n) { cudaFree(ctx->Ainv); ctx->Ainv = nullptr; }
   if (!ctx->Ainv) CU(cudaMalloc((void**)&ctx->Ainv, (size_t)n * n * sizeof(double)));
   if (!ctx->coarse_host) {
+    // Work matrix [A | I] and the elimination's ~2n launches: both persist in the context.  The launches are captured ONCE into a
+    // CUDA graph and replayed per tensor -- issued one by one they depend on the host keeping up for ~1000 launches of ~6 us, and
+    // on B200 boxes whose host threads get descheduled that phase was measured at anything between 6 ms and 830 ms.
     const int ld = 2 * n;
-    double* M = nullptr;
-    double* colk = nullptr;
-    CU(cudaMalloc((void**)&M, (size_t)n * ld * sizeof(double) + (size_t)n * sizeof(double) + 16));
-    colk = M + (size_t)n * ld;
-    int* singular = (int*)(colk + n);
-    cudaMemsetAsync(M, 0, (size_t)n * ld * sizeof(double) + (size_t)n * sizeof(double) + 16, ctx->stream);
-    if (ctx->dim == 3) MAD_LAUNCH((k_coarse_matrix<3>), (n + 127) / 128, 128, 0, ctx->stream, L.g, tensor_of(L), M, n, ld);
-    else MAD_LAUNCH((k_coarse_matrix<2>), (n + 127) / 128, 128, 0, ctx->stream, L.g, tensor_of(L), M, n, ld);
-    const dim3 eg((ld + 255) / 256, (n + 7) / 8);
-    for (int k = 0; k < n; ++k) {
-      MAD_LAUNCH((k_gj_pivot), 1, 1024, 0, ctx->stream, M, n, ld, k, colk, singular);
-      MAD_LAUNCH((k_gj_eliminate), eg, 256, 0, ctx->stream, M, n, ld, k, (const double*)colk);
+    const size_t mbytes = (size_t)n * ld * sizeof(double) + (size_t)n * sizeof(double) + 16;
+    if (ctx->gjM && ctx->gj_n != n) {
+      if (ctx->gj_exec) { cudaGraphExecDestroy(ctx->gj_exec); ctx->gj_exec = nullptr; }
+      cudaFree(ctx->gjM);
+      ctx->gjM = nullptr;
     }
-    cudaMemcpy2DAsync(ctx->Ainv, (size_t)n * sizeof(double), M + n, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), n, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (!ctx->gjM) { CU(cudaMalloc((void**)&ctx->gjM, mbytes)); ctx->gj_n = n; }
+    double* M = ctx->gjM;
+    double* colk = M + (size_t)n * ld;
+    int* singular = (int*)(colk + n);
+    auto enqueue = [&]() {
+      cudaMemsetAsync(M, 0, mbytes, ctx->stream);
+      if (ctx->dim == 3) MAD_LAUNCH((k_coarse_matrix<3>), (n + 127) / 128, 128, 0, ctx->stream, L.g, tensor_of(L), M, n, ld);
+      else MAD_LAUNCH((k_coarse_matrix<2>), (n + 127) / 128, 128, 0, ctx->stream, L.g, tensor_of(L), M, n, ld);
+      const dim3 eg((ld + 255) / 256, (n + 7) / 8);
+      for (int k = 0; k < n; ++k) {
+        MAD_LAUNCH((k_gj_pivot), 1, 1024, 0, ctx->stream, M, n, ld, k, colk, singular);
+        MAD_LAUNCH((k_gj_eliminate), eg, 256, 0, ctx->stream, M, n, ld, k, (const double*)colk);
+      }
+      cudaMemcpy2DAsync(ctx->Ainv, (size_t)n * sizeof(double), M + n, (size_t)ld * sizeof(double), (size_t)n * sizeof(double), n, cudaMemcpyDeviceToDevice, ctx->stream);
+    };
+    bool launched = false;
+    if (ctx->graph_voxels > 0 && !ctx->gj_graph_bad) {
+      if (!ctx->gj_exec) {
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          enqueue();
+          ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&ctx->gj_exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) { cudaGetLastError(); ctx->gj_exec = nullptr; ctx->gj_graph_bad = true; }
+      }
+      if (ctx->gj_exec) {
+        if (cudaGraphLaunch(ctx->gj_exec, ctx->stream) == cudaSuccess) launched = true;
+        else { cudaGetLastError(); ctx->gj_graph_bad = true; }
+      }
+    }
+    if (!launched) enqueue();
+    ctx->launches += 2 * n + 1;
     int sing = 0;
     cudaMemcpyAsync(ctx->h_scalar + 3, singular, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     memcpy(&sing, ctx->h_scalar + 3, sizeof(int));
-    cudaFree(M);
     if (e != cudaSuccess) return fail(ctx, MADGPU_ECUDA, "coarsest-grid inverse: %s", cudaGetErrorString(e));
     if (sing) return fail(ctx, MADGPU_ESINGULAR, "coarsest-grid operator (%d unknowns) is singular", n);
   } else {
@@ -1630,6 +1674,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
   ctx->dim = p->dim;
   ctx->ncomp = p->dim == 2 ? 3 : 6;
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
+  ctx->gjM = nullptr; ctx->gj_n = 0; ctx->gj_exec = nullptr; ctx->gj_graph_bad = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
   ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
   ctx->flags = ctx->flags_lo = ctx->flags_hi = nullptr; ctx->halo_seq = 0; ctx->p2p = false;
@@ -1641,6 +1686,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->fast_min_nx = e ? std::max(atoi(e), 8) : 64;
     e = getenv("MADGPU_FAST2D");
     ctx->fast2d = e ? atoi(e) : 1;
+    e = getenv("MADGPU_FAST2D_MIN_PIXELS");
+    ctx->fast2d_min_pixels = e ? atoll(e) : (1ll << 20);
     e = getenv("MADGPU_PF_DIST");
     ctx->pf_dist = e ? atoi(e) : 2;
     e = getenv("MADGPU_GS_PAIRS");
@@ -1657,6 +1704,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     if ((e = getenv("MADGPU_P2P_TEST_DROP_SIGNAL"))) sscanf(e, "%d:%d", &ctx->p2p_drop_rank, &ctx->p2p_drop_seq);
     e = getenv("MADGPU_RES64_COEF32");
     ctx->res64_c32 = e ? atoi(e) : 1;
+    e = getenv("MADGPU_RES64_MINB");
+    ctx->res64_minb = e ? atoi(e) : 2;
     e = getenv("MADGPU_FAST_CFG");
     ctx->fast_cfg = e ? atoi(e) : 0;
     e = getenv("MADGPU_GRAPH_VOXELS");
@@ -1796,6 +1845,8 @@ void madgpu_destroy(madgpu_ctx* ctx)
   for (int l = 0; l < MADGPU_MAX_LEVELS; ++l)
     for (void* p : ctx->lv[l].allocs) cudaFree(p);
   for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->gj_exec) cudaGraphExecDestroy(ctx->gj_exec);
+  if (ctx->gjM) cudaFree(ctx->gjM);
   if (ctx->Ainv) cudaFree(ctx->Ainv);
   if (ctx->partials) cudaFree(ctx->partials);
   if (ctx->d_scalar) cudaFree(ctx->d_scalar);
@@ -2072,7 +2123,7 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
     const int wy = (ctx->gs_coef16 && !L.coef16_off) ? (gs_pairs(ctx, L) ? 8 : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
     tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
-  } else if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast2(ctx, L)) {
+  } else if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast2_gs(ctx, L)) {
     tile[0] = fast::TX; tile[1] = fast2_yc(L.g); tile[2] = 1;  // 2-D ordering: rows in y order, even then odd columns (mad_fast2d.cuh)
   } else {
     tile[0] = tile[1] = tile[2] = 0;  // one pass per colour over the whole level

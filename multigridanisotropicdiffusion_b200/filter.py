@@ -218,3 +218,7 @@ class VEDMultigridImageFilter:
         if self._output is None:
             self.Update()
         return self._output
+
+    def close(self):
+        """Nothing to release: Update() creates and destroys its device contexts (kept for symmetry with the solver filter)."""
+

@@ -188,9 +188,11 @@ inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t s)
   else std::memset(p, v, bytes);
   return cudaSuccess;
 }
-inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
+inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t s)
 {
-  for (size_t r = 0; r < height; ++r) std::memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width);
+  auto op = [=] { for (size_t r = 0; r < height; ++r) std::memmove((char*)dst + r * dpitch, (const char*)src + r * spitch, width); };
+  if (s && s->rec) s->rec->push_back(op);
+  else op();
   return cudaSuccess;
 }
 inline cudaError_t cudaMallocHost(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }

@@ -155,6 +155,18 @@ def test_device_inverse_of_the_coarsest_operator(MadSolver, monkeypatch, shape, 
     ref = o.direct_solve(fl.astype(np.float64))
     assert rel_l2(res["0"], ref) < 1e-6 and rel_l2(res["1"], ref) < 1e-6
     assert rel_l2(res["0"], res["1"]) < 1e-6
+    # a second tensor on the same context replays the captured elimination on the new operator
+    monkeypatch.setenv("MADGPU_COARSE_HOST", "0")
+    T2 = random_spd_tensor(shape, seed=9)
+    with MadSolver(shape, sp, time_step=0.1, smoother=1, iterations_per_grid=2) as s:
+        s.set_tensor(T)
+        first = s.op_coarse_solve(fl)
+        s.set_tensor(T2)
+        second = s.op_coarse_solve(fl)
+    assert np.array_equal(first, res["0"])
+    o2 = O.Oracle(shape, sp, T2.astype(np.float64), 0.1, smoother=1, nu=2)
+    assert rel_l2(second, o2.direct_solve(fl.astype(np.float64))) < 1e-6
+    assert rel_l2(second, first) > 1e-3
 
 
 def test_operators_and_casts(MadSolver):

@@ -22,6 +22,7 @@ CASES = [
 @pytest.fixture(autouse=True)
 def _streaming_everywhere(monkeypatch):
     monkeypatch.setenv("MADGPU_FAST_MIN_NX", "8")
+    monkeypatch.setenv("MADGPU_FAST2D_MIN_PIXELS", "0")  # default 2^20: small levels keep the one-pixel-per-thread kernels except for Gauss-Seidel
 
 
 def _mk(case, smoother=0, nu=2, seed=0):
@@ -192,3 +193,26 @@ def test_whole_solve_matches_oracle(case, smoother):
     assert all(abs(a - b) <= (0 if smoother == "wj" else 2) for a, b in zip(st["cycles_per_step"], cyc)), (st["cycles_per_step"], cyc)
     assert rel_l2(out, ref) < (1e-5 if smoother == "wj" else 1e-4)
     assert rel_l2(out, ref) < 1e-7
+
+
+def test_default_thresholds_on_a_megapixel_image(monkeypatch):
+    """Default settings (streaming kernels from nx >= 64 and 2^20 pixels; Gauss-Seidel strips at every size): level 0 of a
+    1030 x 1100 image runs k2_sweep / k2_restrict / k2_prolong, the coarser levels the one-pixel-per-thread kernels."""
+    from multigridanisotropicdiffusion_b200 import MadSolver
+    from oracle import oracle as O
+    monkeypatch.delenv("MADGPU_FAST_MIN_NX")
+    monkeypatch.delenv("MADGPU_FAST2D_MIN_PIXELS")
+    shape, sp = (1030, 1100), (1.0, 1.0)
+    T, img = random_spd_tensor(shape, seed=2), random_image(shape, seed=5)
+    for smoother, sm in (("wj", 1), ("gs", 0)):
+        with MadSolver(shape, sp, time_step=0.1, smoother=sm, iterations_per_grid=2, tolerance=1e-9, max_cycles=60) as s:
+            s.set_tensor(T)
+            out = s.solve(img, out_dtype=np.float64)
+            st = s.last_stats
+            if smoother == "gs":
+                assert s.gs_tile(0) is not None and s.gs_tile(0)[2] == 1
+        o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=sm, nu=2)
+        ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-9, max_cycles=60)
+        assert st["final_relres"][0] <= 1e-9
+        assert abs(st["cycles_per_step"][0] - cyc[0]) <= (0 if smoother == "wj" else 2), (st["cycles_per_step"], cyc)
+        assert rel_l2(out, ref) < 1e-7, rel_l2(out, ref)

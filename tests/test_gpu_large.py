@@ -1,12 +1,15 @@
 """Parity at BASELINE.json's sizes against the oracle (itkMultigridAnisotropicDiffusionImageFilter.hxx:207-246 restated in
-oracle/mad_oracle.c): configs[2] = 256^3 and a 512 x 512 x 64 slab of configs[3] (as many tiles of the fused Gauss-Seidel sweep
-per plane as 512^3 has, z-chunks and 32-bit offsets far beyond the small cases of test_gpu_fast.py / test_gpu_solve.py).
+oracle/mad_oracle.c).
 
-The oracle is a scalar fp64 port (~1 Mvoxel/s per pass): its solves run in worker PROCESSES started when the module is first used
--- one per case, side by side on the host cores -- while the GPU does its part; ~2 minutes of wall time in all.
-
+configs[2] = 256^3, whole solves.  The oracle is a scalar fp64 port (~1 Mvoxel/s per pass): its solves run in a worker PROCESS
+started when the module is first used, while the GPU does its part; ~2 minutes of wall time.
   weighted Jacobi : ONE V(3,3) cycle from the same iterate, rel-L2 <= 1e-5 (north_star's per-V-cycle bound)
   Gauss-Seidel    : one time step solved to relres 1e-8 on both sides, rel-L2 of the converged image <= 1e-4
+
+configs[3]'s planes (512 x 512, 12 of them): every level-0 operator of the cycle against the oracle's -- as many tiles of the fused
+Gauss-Seidel sweep per plane, warp columns and row tiles as 512^3 has.  Operator level, because a thin slab stops coarsening at
+6 x 256 x 256 and the oracle's dense coarsest-grid factorisation of 393 k unknowns is out of reach (a 512 x 512 x 64 whole solve
+was tried first and never finished on the oracle's side).
 Size-independent properties at the full 512^3 are in test_gpu_props.py."""
 import concurrent.futures as cf
 import multiprocessing as mp
@@ -20,9 +23,9 @@ pytestmark = pytest.mark.gpu
 
 import os
 
-CASES = {"256": (256, 256, 256), "slab512": (64, 512, 512)}  # (nz, ny, nx)
+CASES = {"256": (256, 256, 256)}  # (nz, ny, nx)
 if os.environ.get("MADGPU_LARGE_TEST_DRYRUN") == "1":  # logic check of this file on the CPU dry-run build (conftest.py): tiny stand-ins
-    CASES = {"256": (24, 24, 64), "slab512": (24, 24, 128)}
+    CASES = {"256": (24, 24, 64)}
 NU, DT, GS_TOL = 3, 0.1, 1e-8
 
 
@@ -78,3 +81,46 @@ def test_baseline_size_parity(name, oracle_results):
     assert e_wj <= 1e-5
     assert st["final_relres"][0] <= GS_TOL and abs(st["cycles_per_step"][0] - cyc[0]) <= 2
     assert e_gs <= 1e-4
+
+
+PLANES512 = (12, 512, 512) if os.environ.get("MADGPU_LARGE_TEST_DRYRUN") != "1" else (12, 24, 136)
+
+
+def test_operators_on_512_wide_planes():
+    from multigridanisotropicdiffusion_b200 import MadSolver, phantom
+    from oracle import oracle as O
+    from util import gs_leg_model, random_image
+    shape = PLANES512
+    img, T = _inputs(shape)
+    o = O.Oracle(shape, phantom.VED_SPACING, T.astype(np.float64), DT, smoother=1, nu=NU, max_coarse=2000)
+    u, f = random_image(shape, seed=1), random_image(shape, seed=2)
+    u64, f64 = u.astype(np.float64), f.astype(np.float64)
+    with MadSolver(shape, phantom.VED_SPACING, time_step=DT, smoother=MadSolver.WJ, iterations_per_grid=NU) as s:
+        s.set_tensor(T)
+        # weighted Jacobi sweep, fp32 residual, fp64 stop-test residual (k_fast_sweep)
+        e = rel_l2(s.op_smooth(0, u, f, smoother=1, n_iter=1), o.smooth(0, u64, f64))
+        assert e < 2e-6, e
+        g, nrm = s.op_residual(0, u, f)
+        r = o.residual(0, u64, f64)
+        assert np.abs(g - r).max() < 4e-6 * np.abs(u).max() * 12.0
+        _, nrm64 = s.op_residual_f64(u64, f64, norm_only=True)
+        assert abs(nrm64 - np.linalg.norm(r)) < 2e-6 * np.linalg.norm(r)
+        # transfers (k_fast_restrict_cell, k_fast_prolong_cell: all axes cell-centred)
+        cent = s.levels[1]["centering"]
+        e = rel_l2(s.op_restrict(0, u), O.restrict(u64, cent))
+        assert e < 3e-7, e
+        c = random_image(s.levels[1]["shape"], seed=3)
+        e = rel_l2(s.op_prolong(0, c), O.interpolate(c.astype(np.float64), cent))
+        assert e < 3e-7, e
+    # the fused Gauss-Seidel leg (k_coef_gs2, packed fp16 rows) against the numpy model of its documented ordering
+    with MadSolver(shape, phantom.VED_SPACING, time_step=DT, smoother=MadSolver.GS, iterations_per_grid=NU) as s:
+        s.set_tensor(T)
+        tile = s.gs_tile(0)
+        assert tile is not None and tile[0] == 128 and tile[1] == 8
+        plan = s.gs_leg_plan(0, 2)
+        g = s.op_smooth(0, u, f, smoother=0, n_iter=2)
+        S = o.stencil(0)
+        r = gs_leg_model(S, u64, f64, plan)
+        e = rel_l2(g, r)
+        print(f"[planes512] GS leg of 2 sweeps vs the ordering model: rel-L2 {e:.3e}, plan {plan}")
+        assert e < 4e-3, e  # the packed rows round the operator to 11 bits (test_gpu_fast.py: 2e-3 per sweep)

@@ -162,9 +162,10 @@ def test_vcycle_weighted_jacobi(case, nu):
 
 @pytest.mark.parametrize("case", [CASES_3D[1], CASES_2D[0]])
 @pytest.mark.parametrize("ncolors", [4, 8])
-def test_multicolour_gs_is_a_gauss_seidel_ordering(case, ncolors):
+def test_multicolour_gs_is_a_gauss_seidel_ordering(case, ncolors, monkeypatch):
     """One multicolour sweep == sequential Gauss-Seidel in colour-major order (checked on the CPU with the
     oracle's explicit operator rows): the colouring has no intra-colour coupling."""
+    monkeypatch.setenv("MADGPU_FAST2D", "0")  # the 64-pixel-wide 2-D case would otherwise get the strip sweep of mad_fast2d.cuh (tests/test_gpu_fast2d.py)
     from multigridanisotropicdiffusion_b200 import MadSolver
     from oracle import oracle as O
     shape, sp, dt = case
