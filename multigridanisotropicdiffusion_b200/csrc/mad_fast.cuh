@@ -580,6 +580,177 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 
 
 // ------------------------------------------------------------------------------------------
+// Level-0 fp64 defect / stop-test residual with the y-neighbour rows in SHARED MEMORY (k_fast_res64).
+//
+// k_fast_sweep<MODE_RES_C32, double> keeps three planes x three rows x six fp64 values of u per thread: 255 registers, 8 warps
+// per SM, and ncu shows it waiting on latency (issue slots 35 % busy) at 0.55 of the copy bandwidth.  Here a thread keeps only
+// its OWN row of the three live planes (18 doubles); the rows y-1 / y+1 come from a ring of four planes of the CTA's tile of
+// rows (WY rows + one halo row below and above) in shared memory, which every warp fills with the row it loads anyway (the
+// first and the last warp also load the halo row).  The plane two steps ahead is loaded while the current one is evaluated;
+// one __syncthreads per plane step.  Arithmetic as MODE_RES_C32: operator row evaluated in fp32 from the tensor planes (the
+// row the fp32 sweeps relax), applied in fp64 to the fp64 iterate; out = fp32 residual, partials = per-CTA sums of squares.
+// Row layout in shared memory: A[32] = the lanes' voxels 0,1 (double2), B[32] = voxels 2,3, then the two x-halo voxels of the
+// warp ends -- 16-byte accesses at a stride of 16 bytes, no bank conflicts; x-neighbours by shuffle as everywhere else.
+// grid = (ceil(nx/128), ceil(ny/WY), ceil(nz/zc)), block = (32, WY).
+// ------------------------------------------------------------------------------------------
+constexpr int R64_ROW = 130;  // doubles per tile row: 64 (A) + 64 (B) + halo left + halo right
+template <int WY>
+struct Res64Smem {
+  double v[4][WY + 2][R64_ROW];
+};
+__device__ __forceinline__ void r64_store_row(double* __restrict__ row, const Raw6<double>& r, int lane)
+{
+  reinterpret_cast<double2*>(row)[lane] = r.c.a;
+  reinterpret_cast<double2*>(row + 64)[lane] = r.c.b;
+  if (lane == 0) row[128] = r.h;
+  if (lane == 31) row[129] = r.h;
+}
+__device__ __forceinline__ Raw6<double> r64_load_row6(const double* __restrict__ row, int lane)
+{
+  Raw6<double> r;
+  r.c.a = reinterpret_cast<const double2*>(row)[lane];
+  r.c.b = reinterpret_cast<const double2*>(row + 64)[lane];
+  r.h = lane == 0 ? row[128] : row[129];  // only the two warp-end lanes use it
+  return r;
+}
+__device__ __forceinline__ V4<double> r64_load_row4(const double* __restrict__ row, int lane)
+{
+  const double2 a = reinterpret_cast<const double2*>(row)[lane], b = reinterpret_cast<const double2*>(row + 64)[lane];
+  V4<double> w;
+  w.v[0] = a.x; w.v[1] = a.y; w.v[2] = b.x; w.v[3] = b.y;
+  return w;
+}
+
+template <int WY, int MINB>
+__global__ void __launch_bounds__(32 * WY, MINB) k_fast_res64(Geom g, Tensor D, const double* __restrict__ u, const double* __restrict__ f,
+                                                                float* __restrict__ out, double* __restrict__ partials, int zc, int pfd)
+{
+  __shared__ Res64Smem<WY> sm;
+  const Pos p = make_pos(g);
+  const int w = threadIdx.y, lane = p.lane;
+  const int y0t = blockIdx.y * WY;
+  const bool valid = p.y < g.ny;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
+  // tile rows (slot 0 = image row y0t - 1) that hold this warp's mirrored y-1 / y+1 rows: row -1 is row 1, row ny is row ny - 2
+  const int rm = p.y == 0 ? 2 : w, rp = p.y == g.ny - 1 ? w : w + 2;
+  // the halo rows of the tile: loaded by the first / last warp when they exist
+  const bool halo_lo = w == 0 && y0t > 0, halo_hi = w == WY - 1 && y0t + WY < g.ny;
+  const int rowo = (valid ? p.y : 0) * g.pitch + p.xl;
+  const int rowo_lo = (y0t - 1) * g.pitch + p.xl, rowo_hi = (y0t + WY) * g.pitch + p.xl;
+  // logical plane L (z0 - 1 .. z1) -> ring slot; its physical plane is the node mirror at the two physical ends
+  auto slot_of = [&](int L) { return (L - (z0 - 1)) & 3; };
+  auto phys = [&](int L) { return L < z0 ? zmirror_lo(g, z0) : (L >= g.nz ? zmirror_hi(g, g.nz - 1) : L); };
+  struct PlaneRaw { Raw6<double> own, lo, hi; };
+  auto issue_plane = [&](int L) {
+    PlaneRaw r;
+    const int b = phys(L) * (int)g.plane;
+    r.own.c.a = r.own.c.b = make_double2(0.0, 0.0);
+    r.own.h = 0.0;
+    if (valid) r.own = issue6(u, b + rowo, p);
+    r.lo = r.own; r.hi = r.own;
+    if (halo_lo) r.lo = issue6(u, b + rowo_lo, p);
+    if (halo_hi) r.hi = issue6(u, b + rowo_hi, p);
+    return r;
+  };
+  auto publish_plane = [&](int L, const PlaneRaw& r) {  // raw rows -> the ring; returns nothing, the own row is finished by the caller
+    const int s = slot_of(L);
+    if (valid) r64_store_row(sm.v[s][w + 1], r.own, lane);
+    if (halo_lo) r64_store_row(sm.v[s][0], r.lo, lane);
+    if (halo_hi) r64_store_row(sm.v[s][WY + 1], r.hi, lane);
+  };
+  auto own_row = [&](const PlaneRaw& r) {
+    V6<double> v = finish6<double, double>(r.own, p);
+    if (p.xb) mirror_x(v, p.xt, p.jl);
+    return v;
+  };
+  auto nb_row6 = [&](int L, int r) {
+    V6<double> v = finish6<double, double>(r64_load_row6(sm.v[slot_of(L)][r], lane), p);
+    if (p.xb) mirror_x(v, p.xt, p.jl);
+    return v;
+  };
+  double sq = 0.0;
+  const Prefetch PFL = make_prefetch(g, D, u, f, lane, valid ? p.y : 0);
+  const int zpf_end = min(z1 + 1, g.nz);
+  V6<double> um, uc, up;
+  DzState S;
+  {
+    const PlaneRaw r0 = issue_plane(z0 - 1), r1 = issue_plane(z0), r2 = issue_plane(z0 + 1);
+    const int o_m = zmirror_lo(g, z0) * (int)g.plane + rowo, o_c = z0 * (int)g.plane + rowo;
+    publish_plane(z0 - 1, r0); publish_plane(z0, r1); publish_plane(z0 + 1, r2);
+    um = own_row(r0); uc = own_row(r1); up = own_row(r2);
+    if (valid) {
+      const DzRaw d0 = issue_dz(D, o_m, p), d1 = issue_dz(D, o_c, p);
+      S.xz_m = finish4<float>(d0.xz.c); S.yz_m = finish4<float>(d0.yz); S.zz_m = finish4<float>(d0.zz);
+      S.xz_c = finish6<float, float>(d1.xz, p); S.yz_c = finish4<float>(d1.yz); S.zz_c = finish4<float>(d1.zz);
+    }
+  }
+  __syncthreads();
+  for (int z = z0; z < z1; ++z) {
+    const int oc = z * (int)g.plane + rowo, on = zmirror_hi(g, z) * (int)g.plane + rowo;
+    if (pfd > 0 && z + pfd < zpf_end && valid) prefetch_plane(PFL, z + pfd);
+    // ---- every load of the step: u of the plane after next, the tensor rows of this step, f ----
+    const bool more = z + 1 < z1;
+    PlaneRaw rn;
+    if (more) rn = issue_plane(z + 2);
+    if (valid) {
+      const DzRaw dz = issue_dz(D, on, p);
+      const DcRaw dc = issue_dc(D, oc, p);
+      const Raw4<double> rf = issue4(f, oc);
+      S.xz_p = finish6<float, float>(dz.xz, p); S.yz_p = finish4<float>(dz.yz); S.zz_p = finish4<float>(dz.zz);
+      const DcFin F = finish_dc(dc, p);
+      const V4<double> fv = finish4<double>(rf);
+      Coef<float> c;
+      coefficients<float>(g, D, p, z, oc, S, F, c);
+      double acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // own rows of the three planes
+        double s = (double)c.xp[j] * uc.v[j + 2] + (double)c.xm[j] * uc.v[j] + (double)c.zp[j] * up.v[j + 1] + (double)c.zm[j] * um.v[j + 1];
+        s += (double)c.exz[j] * ((up.v[j + 2] - um.v[j + 2]) - (up.v[j] - um.v[j]));
+        acc[j] = fv.v[j] - (double)c.diag[j] * uc.v[j + 1] - s;
+      }
+      {  // rows y+1, y-1 of this plane
+        const V6<double> q2 = nb_row6(z, rp), q0 = nb_row6(z, rm);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[j] -= (double)c.yp[j] * q2.v[j + 1] + (double)c.ym[j] * q0.v[j + 1] + (double)c.exy[j] * ((q2.v[j + 2] - q0.v[j + 2]) - (q2.v[j] - q0.v[j]));
+      }
+      {  // rows y+1, y-1 of the planes above and below
+        const V4<double> n2 = r64_load_row4(sm.v[slot_of(z + 1)][rp], lane), m2 = r64_load_row4(sm.v[slot_of(z - 1)][rp], lane);
+        const V4<double> n0 = r64_load_row4(sm.v[slot_of(z + 1)][rm], lane), m0 = r64_load_row4(sm.v[slot_of(z - 1)][rm], lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] -= (double)c.eyz[j] * ((n2.v[j] - m2.v[j]) - (n0.v[j] - m0.v[j]));
+      }
+      float res[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        res[j] = (float)acc[j];
+        if (p.xt + j < g.nx) sq += acc[j] * acc[j];
+      }
+      if (out && p.xt < g.nx) {
+        store4<float>(out, oc, p.xt, g.nx, res);
+        store_ghosts<float>(g, z, rowo, p.xt, res);
+      }
+    }
+    // ---- the plane after next joins the ring (its slot was last read one step ago) ----
+    um = uc; uc = up;
+    if (more) {
+      publish_plane(z + 2, rn);
+      up = own_row(rn);
+    }
+    if (valid) {
+      S.xz_m = mid4(S.xz_c); S.yz_m = S.yz_c; S.zz_m = S.zz_c;
+      S.xz_c = S.xz_p; S.yz_c = S.yz_p; S.zz_c = S.zz_p;
+    }
+    __syncthreads();
+  }
+  if (partials) {
+    const double t = block_sum(sq);
+    if (threadIdx.x == 0 && threadIdx.y == 0)
+      partials[(size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Gauss-Seidel sweep (mad/itkMultigridGaussSeidelSmoother.hxx:33-111) in ONE pass over the volume.
 // Ordering: planes in z order (as the reference's outer loop); inside a plane the even rows first
 // (even x, then odd x), then the odd rows -- the four in-plane colours of the 9-point plane stencil,
@@ -1483,16 +1654,21 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict_cell(Geom gf, Geom gc
   for (int ky = 0; ky < 4; ++ky) ro[ky] = min(max(2 * yc + ky - 1, 0), gf.ny - 1) * gf.pitch + p.xl;
   const int zlo = gf.zlo_phys ? 0 : -1, zhi = gf.zhi_phys ? gf.nz - 1 : gf.nz;  // ghost planes of a z-slab are valid
   struct P2 { float a, b; };
-  // xy-restricted row of fine plane z (clamped into the valid planes; a clamped plane only ever meets weight 0)
-  auto plane = [&](int z) {
+  // the four rows of fine plane z (clamped into the valid planes; a clamped plane only ever meets weight 0): loads only ...
+  struct PR { Raw6<float> r[4]; };
+  auto issue_plane = [&](int z) {
     const int zb = min(max(z, zlo), zhi) * (int)gf.plane;
-    Raw6<float> rw[4];
+    PR q;
 #pragma unroll
-    for (int ky = 0; ky < 4; ++ky) rw[ky] = issue6(fine, zb + ro[ky], p);
+    for (int ky = 0; ky < 4; ++ky) q.r[ky] = issue6(fine, zb + ro[ky], p);
+    return q;
+  };
+  // ... and their xy-restricted row
+  auto finish_plane = [&](const PR& q) {
     P2 o = {0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const V6<float> v = finish6<float, float>(rw[ky], p);
+      const V6<float> v = finish6<float, float>(q.r[ky], p);
       float m[6];  // voxels beyond the fine row only ever meet zero weights, but may hold anything: mask them
 #pragma unroll
       for (int i = 0; i < 6; ++i) { const int fx = p.xt - 1 + i; m[i] = (fx >= 0 && fx < gf.nx) ? v.v[i] : 0.f; }
@@ -1501,9 +1677,18 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict_cell(Geom gf, Geom gc
     }
     return o;
   };
-  P2 pm = plane(2 * k0 - 1), p0 = plane(2 * k0);
+  P2 pm, p0;
+  {
+    const PR ra = issue_plane(2 * k0 - 1), rb = issue_plane(2 * k0);
+    pm = finish_plane(ra);
+    p0 = finish_plane(rb);
+  }
+  // the loads of the next coarse plane's two fine planes are in flight while this one is reduced
+  PR r1 = issue_plane(2 * k0 + 1), r2 = issue_plane(2 * k0 + 2);
   for (int k = k0; k < k1; ++k) {
-    const P2 p1 = plane(2 * k + 1), p2 = plane(2 * k + 2);
+    PR n1 = r1, n2 = r2;
+    if (k + 1 < k1) { n1 = issue_plane(2 * k + 3); n2 = issue_plane(2 * k + 4); }
+    const P2 p1 = finish_plane(r1), p2 = finish_plane(r2);
     float wz[4];
     restrict_taps(k, gc.nz, 1, wz, gc.zlo_phys != 0, gc.zhi_phys != 0);
     const float b0 = wz[0] * pm.a + wz[1] * p0.a + wz[2] * p1.a + wz[3] * p2.a;
@@ -1511,6 +1696,7 @@ __global__ void __launch_bounds__(32 * WY) k_fast_restrict_cell(Geom gf, Geom gc
     const long long oo = (long long)k * gc.plane + (long long)yc * gc.pitch + xc0;
     if (xc0 + 1 < gc.nx) *reinterpret_cast<float2*>(coarse + oo) = make_float2(b0, b1);
     else if (xc0 < gc.nx) coarse[oo] = b0;
+    r1 = n1; r2 = n2;
     pm = p1; p0 = p2;
   }
 }

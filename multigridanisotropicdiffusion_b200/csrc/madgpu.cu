@@ -144,6 +144,7 @@ struct madgpu_ctx {
   int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
+  int res64_smem;   // MADGPU_RES64_SMEM: 0 = all-register fp64 residual (k_fast_sweep<MODE_RES_C32>), 3 / 4 = k_fast_res64 capped for 3 / 4 CTAs per SM
   int res64_minb;   // MADGPU_RES64_MINB=3: register cap of the fp64 residual for 3 CTAs per SM
   int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 -- the row the fp32 sweeps relax -- and applied in fp64 (default; MADGPU_RES64_COEF32=0: fp64 row)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
@@ -161,6 +162,7 @@ struct madgpu_ctx {
   };
   std::vector<CycleGraph> graphs;
   long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
+  int gs_tb_single;        // MADGPU_GS_TB_SINGLE=1: every sweep through k_coef_gs_tb<1> (shared-memory ring fed by cp.async, tiles of 128 x 16) instead of k_coef_gs2: A/B hook
   int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB = 2 or 3; default 1 = off:
                            // measured on B200 at 512^3 a fused pass of 3 sweeps takes 2.04 ms against 3 x 0.77 ms -- the packed rows of the older planes
                            // come from L2, not HBM, but still cross the L2 -> SM fabric once per sweep -- and its frozen tile faces cost 3 V-cycles in 6)
@@ -563,7 +565,7 @@ void op_zero(madgpu_ctx* ctx, Level& L, float* p)
 constexpr int TB_WP = 8;  // warps (row pairs) per CTA: tiles of 128 x 16 voxels
 bool use_tb(const madgpu_ctx* ctx, const Level& L)
 {
-  return ctx->gs_tb > 1 && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && use_fast(ctx, L) && gs_pairs(ctx, L) && L.g.ny >= 8 && L.g.nz >= 8;
+  return (ctx->gs_tb > 1 || ctx->gs_tb_single) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && use_fast(ctx, L) && gs_pairs(ctx, L) && L.g.ny >= 8 && L.g.nz >= 8;
 }
 // planes per CTA: ~4 waves of the two resident CTAs per SM; long chunks keep the fill / drain steps of the sweep pipeline (2 per
 // fused sweep) and the frozen z faces rare
@@ -656,10 +658,11 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
     } else if (use_fast(ctx, L) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && build_coef16(ctx, L)) {
       // fused sweep fed by pre-evaluated fp16 operator rows (built once per tensor and level)
       Scope s(ctx, cls);
-      const int fuse = use_tb(ctx, L) ? tb_fuse(ctx, n_iter - it) : 1;
-      if (fuse > 1) {  // `fuse` sweeps of this leg in one pass (temporal blocking)
+      const int fuse = use_tb(ctx, L) ? tb_fuse(ctx, n_iter - it) : 0;
+      if (fuse >= 1) {  // `fuse` sweeps of this leg in one pass over shared-memory plane rings (temporal blocking; 1: MADGPU_GS_TB_SINGLE)
         if (fuse == 3) launch_tb<3>(ctx, L, gg, uz);
-        else launch_tb<2>(ctx, L, gg, uz);
+        else if (fuse == 2) launch_tb<2>(ctx, L, gg, uz);
+        else launch_tb<1>(ctx, L, gg, uz);
         it += fuse - 1;
       } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
         const int zc = fast_zc(L.g, 8);
@@ -778,6 +781,18 @@ void op_residual64(madgpu_ctx* ctx, float* r32_or_null, double* r64_or_null)
   if (r64_or_null) {
     if (ctx->dim == 3) MAD_LAUNCH((k_residual<3, double, double, double, double>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
     else MAD_LAUNCH((k_residual<2, double, double, double, double>), g, b, 0, ctx->stream, L.g, D, ctx->u64, ctx->f64, r64_or_null, ctx->partials);
+  } else if (use_fast(ctx, L) && ctx->res64_c32 && ctx->res64_smem) {
+    // y-neighbour rows through a shared-memory ring (k_fast_res64): a third of the registers of the all-register form
+    constexpr int WY = 4;
+    const int zc = fast_zc(L.g, WY);
+    const dim3 fg = fast_grid(L.g, WY, zc);
+    Geom gg = L.g;
+    set_ghosts(ctx, gg, L, r32_or_null, sizeof(float));
+    if (ctx->res64_smem == 4) MAD_LAUNCH((fast::k_fast_res64<WY, 4>), fg, dim3(32, WY), 0, ctx->stream, gg, D, (const double*)ctx->u64, (const double*)ctx->f64, r32_or_null, ctx->partials, zc, ctx->pf_dist);
+    else MAD_LAUNCH((fast::k_fast_res64<WY, 3>), fg, dim3(32, WY), 0, ctx->stream, gg, D, (const double*)ctx->u64, (const double*)ctx->f64, r32_or_null, ctx->partials, zc, ctx->pf_dist);
+    halo_signal(ctx, r32_or_null);
+    reduce_partials(ctx, (size_t)fg.x * fg.y * fg.z);
+    return;
   } else if (use_fast(ctx, L)) {
     const size_t nb = ctx->res64_c32 ? launch_fast<fast::MODE_RES_C32, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f)
                                      : launch_fast<fast::MODE_RES, double, double, double, float>(ctx, L, ctx->u64, ctx->f64, r32_or_null, ctx->partials, 0.f);
@@ -1704,6 +1719,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     if ((e = getenv("MADGPU_P2P_TEST_DROP_SIGNAL"))) sscanf(e, "%d:%d", &ctx->p2p_drop_rank, &ctx->p2p_drop_seq);
     e = getenv("MADGPU_RES64_COEF32");
     ctx->res64_c32 = e ? atoi(e) : 1;
+    e = getenv("MADGPU_RES64_SMEM");
+    ctx->res64_smem = e ? atoi(e) : 3;
     e = getenv("MADGPU_RES64_MINB");
     ctx->res64_minb = e ? atoi(e) : 2;
     e = getenv("MADGPU_FAST_CFG");
@@ -1717,6 +1734,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->restrict_cell = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_TB");
     ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 1;
+    e = getenv("MADGPU_GS_TB_SINGLE");
+    ctx->gs_tb_single = e ? atoi(e) : 0;
     e = getenv("MADGPU_COARSE_HOST");
     ctx->coarse_host = e ? atoi(e) : 0;
     e = getenv("MADGPU_COARSE_DIRECT_MAX");
@@ -2104,7 +2123,7 @@ int madgpu_gs_leg_plan(const madgpu_ctx* ctx, int32_t level, int32_t n_iter, int
     madgpu_gs_tile(ctx, level, tile);
     const bool tb_ok = ctx->p.smoother == MADGPU_SMOOTHER_GS && use_tb(ctx, L);
     const int fuse = tb_ok ? tb_fuse(ctx, n_iter - it) : 1;
-    if (fuse > 1) {
+    if (tb_ok) {
       const int zc = tb_zc(L.g);
       q[0] = fuse; q[1] = fast::TX; q[2] = 2 * TB_WP; q[3] = zc; q[4] = flip ? TB_WP : 0; q[5] = flip ? zc / 2 : 0;
       flip ^= 1;

@@ -143,6 +143,9 @@ VED_HD double rg_anti_step(RgState& s, const RgCoefs& c, double x)
 // One whole line, K filters of the same input: x[i * stride] -> out[k][i * stride] (fp32 storage, fp64 recursion).  The causal
 // pass stores its result, the anticausal pass adds to it and applies scale[k].  in must not alias any out[k].
 // This is the body of k_rg_lines (ved.cu); k_rg_rows runs the same sequence of steps per row through shared-memory tiles.
+// Loads are batched RG_BATCH elements ahead of the recursion: the outputs may alias the input as far as the compiler can tell, so a
+// load placed after a store has to wait for it -- one memory latency per element, which bounded k_rg_lines at 1.2-1.4 TB/s.
+constexpr int RG_BATCH = 8;
 template <int K>
 VED_HD void rg_line(const float* __restrict__ x, long long stride, int n, const RgCoefs* c, float* const* out, const double* scale)
 {
@@ -150,22 +153,38 @@ VED_HD void rg_line(const float* __restrict__ x, long long stride, int n, const 
   const double e0 = (double)x[0];
 VED_UNROLL
   for (int k = 0; k < K; ++k) rg_causal_init(s[k], c[k], e0);
-VED_UNROLL4
-  for (int i = 0; i < n; ++i) {
-    const double xi = (double)x[(long long)i * stride];
+  for (int i0 = 0; i0 < n; i0 += RG_BATCH) {
+    float xb[RG_BATCH];
 VED_UNROLL
-    for (int k = 0; k < K; ++k) out[k][(long long)i * stride] = (float)rg_causal_step(s[k], c[k], xi);
+    for (int j = 0; j < RG_BATCH; ++j) xb[j] = i0 + j < n ? x[(long long)(i0 + j) * stride] : 0.f;
+VED_UNROLL
+    for (int j = 0; j < RG_BATCH; ++j) {
+      if (i0 + j < n) {
+        const double xi = (double)xb[j];
+VED_UNROLL
+        for (int k = 0; k < K; ++k) out[k][(long long)(i0 + j) * stride] = (float)rg_causal_step(s[k], c[k], xi);
+      }
+    }
   }
   const double e1 = (double)x[(long long)(n - 1) * stride];
 VED_UNROLL
   for (int k = 0; k < K; ++k) rg_anti_init(s[k], c[k], e1);
-VED_UNROLL4
-  for (int i = n - 1; i >= 0; --i) {
-    const double xi = (double)x[(long long)i * stride];
+  for (int i0 = n - 1; i0 >= 0; i0 -= RG_BATCH) {
+    float xb[RG_BATCH], ob[K][RG_BATCH];
 VED_UNROLL
-    for (int k = 0; k < K; ++k) {
-      float* o = out[k] + (long long)i * stride;
-      *o = (float)(((double)*o + rg_anti_step(s[k], c[k], xi)) * scale[k]);
+    for (int j = 0; j < RG_BATCH; ++j) {
+      const bool in = i0 - j >= 0;
+      xb[j] = in ? x[(long long)(i0 - j) * stride] : 0.f;
+VED_UNROLL
+      for (int k = 0; k < K; ++k) ob[k][j] = in ? out[k][(long long)(i0 - j) * stride] : 0.f;
+    }
+VED_UNROLL
+    for (int j = 0; j < RG_BATCH; ++j) {
+      if (i0 - j >= 0) {
+        const double xi = (double)xb[j];
+VED_UNROLL
+        for (int k = 0; k < K; ++k) out[k][(long long)(i0 - j) * stride] = (float)(((double)ob[k][j] + rg_anti_step(s[k], c[k], xi)) * scale[k]);
+      }
     }
   }
 }
