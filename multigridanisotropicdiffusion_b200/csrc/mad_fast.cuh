@@ -581,6 +581,9 @@ __global__ void __launch_bounds__(32 * WY, MINB) k_fast_sweep(Geom g, Tensor D, 
 
 // ------------------------------------------------------------------------------------------
 // Level-0 fp64 defect / stop-test residual with the y-neighbour rows in SHARED MEMORY (k_fast_res64).
+// MEASURED AND NOT THE DEFAULT (MADGPU_RES64_SMEM=3 selects it): 2.16 ms at 512^3 on B200 against 1.66 ms for the all-register form
+// it was meant to replace -- 12 instead of 8 warps per SM, but a CTA-wide barrier per plane step and 0.6 short-scoreboard stalls per
+// issue on the ring (profiles/r02h_res64_smem_512_full.txt).
 //
 // k_fast_sweep<MODE_RES_C32, double> keeps three planes x three rows x six fp64 values of u per thread: 255 registers, 8 warps
 // per SM, and ncu shows it waiting on latency (issue slots 35 % busy) at 0.55 of the copy bandwidth.  Here a thread keeps only
@@ -1177,6 +1180,13 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
 constexpr int TB_ROWF = 136;  // floats per tile row: [3] = x0-1, [4..131] = the 128 voxels, [132] = x0+128
 __host__ __device__ constexpr int tb_planes(int S) { return 2 * S + 2; }
 __host__ __device__ constexpr size_t tb_smem_bytes(int S, int WP) { return (size_t)tb_planes(S) * (2 * WP + 2) * TB_ROWF * sizeof(float); }
+// STAGE (single sweeps only): the packed rows and f of the planes t, t+1, t+2 are staged in shared memory as well, by cp.async two
+// planes ahead of their use -- loads in flight without a register destination, which is what the register-bound k_coef_gs2 lacks
+constexpr int TB_STAGE_DEPTH = 3;
+__host__ __device__ constexpr size_t tb_stage_bytes(int WP)  // + one more plane of the u ring
+{
+  return (size_t)TB_STAGE_DEPTH * 2 * WP * (32 * COEF_WORDS * 16 + 128 * sizeof(float)) + (size_t)(2 * WP + 2) * TB_ROWF * sizeof(float);
+}
 
 #ifndef MAD_HOST_EMULATION
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src)
@@ -1188,10 +1198,21 @@ __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async16u(uint4* dst_smem, const uint4* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 #else  // the CPU test build copies at issue time
 inline void cp_async16(float* dst, const float* src) { for (int i = 0; i < 4; ++i) dst[i] = src[i]; }
 inline void cp_async4(float* dst, const float* src) { dst[0] = src[0]; }
 inline void cp_async_wait_all() {}
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait_group() {}
+inline void cp_async16u(uint4* dst, const uint4* src) { *dst = *src; }
 #endif
 
 // six consecutive values x-1 .. x+4 of a tile row (the thread's four voxels and their x-neighbours)
@@ -1231,13 +1252,16 @@ __device__ __forceinline__ float offdiag16_tb(const CoefRaw& c, const TbNb& n, i
   return s;
 }
 
-template <int S, int WP, int MINB>
+template <int S, int WP, int MINB, bool STAGE = false>
 __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs_tb(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
                                                                 const float* __restrict__ f, float* __restrict__ out, int zc, int oy, int oz,
                                                                 int pfd, int uzero)
 {
-  constexpr int TY = 2 * WP, NP = tb_planes(S), ROWS = TY + 2;
-  MAD_DYNAMIC_SHARED(float, smem);  // [NP][ROWS][TB_ROWF]
+  static_assert(!STAGE || S == 1, "staged operands: single sweeps only");
+  constexpr int TY = 2 * WP, NP = tb_planes(S) + (STAGE ? 1 : 0), ROWS = TY + 2;  // STAGE: u runs one plane further ahead
+  MAD_DYNAMIC_SHARED(float, smem);  // [NP][ROWS][TB_ROWF], then (STAGE) [DEPTH][TY][32][COEF_WORDS] uint4 and [DEPTH][TY][128] float
+  uint4* const scoef = reinterpret_cast<uint4*>(smem + (size_t)NP * ROWS * TB_ROWF);
+  float* const sf = reinterpret_cast<float*>(scoef + (size_t)TB_STAGE_DEPTH * TY * 32 * COEF_WORDS);
   const int lane = threadIdx.x, w = threadIdx.y;
   Pos p;
   p.lane = lane;
@@ -1274,11 +1298,36 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs_tb(Geom g, const uint
     if (w == 0) load_row(pz, slot, 0, y0 - 1);
     if (w == WP - 1) load_row(pz, slot, TY + 1, y0 + TY);
   };
+  // STAGE: packed rows and f of the warp's two rows of plane pz -> slot pz % DEPTH (every thread copies what it will read itself)
+  auto stage_slot = [&](int pz) { return (pz - z0) % TB_STAGE_DEPTH; };
+  auto stage_plane = [&](int pz) {
+    if (!STAGE || !valid || pz >= z1 || p.xt >= g.nx) return;
+    const int sl = stage_slot(pz);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4* src = coef + coef_quad(g, p.xt >> 2, ya + h, pz) * COEF_WORDS;
+      uint4* dst = scoef + (((size_t)sl * TY + 2 * w + h) * 32 + lane) * COEF_WORDS;
+#pragma unroll
+      for (int i = 0; i < COEF_WORDS; ++i) cp_async16u(dst + i, src + i);
+      cp_async16(sf + ((size_t)sl * TY + 2 * w + h) * 128 + 4 * lane, f + (long long)pz * g.plane + (long long)(ya + h) * g.pitch + p.xt);
+    }
+  };
   if (uzero) {  // the iterate is identically zero (first sweeps of a leg): nothing is loaded, the ring starts as zeros
     for (int i = (w * 32 + lane) * 4; i < NP * ROWS * TB_ROWF; i += 32 * WP * 4)
       *reinterpret_cast<float4*>(smem + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     for (int pz = zmin_load; pz <= min(z0 + 1, zmax_load); ++pz) load_plane(pz);
+  }
+  if (STAGE) {
+    // one commit group per plane step: the group of step t holds the operands of plane t + 2 and u of plane t + 3; at the end of a
+    // step everything but its own group has landed -- the operands of plane t + 1 and u up to plane t + 2, what step t + 1 reads
+    stage_plane(z0);
+    cp_async_commit();
+    if (!uzero && z0 + 2 <= zmax_load) load_plane(z0 + 2);
+    stage_plane(z0 + 1);
+    cp_async_commit();
+    cp_async_wait_group<1>();
+  } else {
     cp_async_wait_all();
   }
   __syncthreads();
@@ -1290,9 +1339,20 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs_tb(Geom g, const uint
   // relax the four voxels of the thread in tile row r (image row y) of plane pc with sweep s
   auto relax = [&](int s, int pc, int r, int y, int rm, int rp) {
     const int zm = (pc == 0 && g.zlo_phys) ? pc + 1 : pc - 1, zp = (pc == g.nz - 1 && g.zhi_phys) ? pc - 1 : pc + 1;
-    const CoefRaw c = issue_coef(coef, g, p, y, pc);
     const int o = pc * (int)g.plane + y * g.pitch + p.xl;
-    const V4<float> fv = finish4<float>(issue4(f, o));
+    CoefRaw c;
+    V4<float> fv;
+    if (STAGE) {
+      const int sl = stage_slot(pc), tr = r - 1;  // tile row 1 = the tile's first image row
+      const uint4* q = scoef + (((size_t)sl * TY + tr) * 32 + lane) * COEF_WORDS;
+#pragma unroll
+      for (int i = 0; i < COEF_WORDS; ++i) c.w[i] = q[i];
+      const float4 t4 = *reinterpret_cast<const float4*>(sf + ((size_t)sl * TY + tr) * 128 + 4 * lane);
+      fv.v[0] = t4.x; fv.v[1] = t4.y; fv.v[2] = t4.z; fv.v[3] = t4.w;
+    } else {
+      c = issue_coef(coef, g, p, y, pc);
+      fv = finish4<float>(issue4(f, o));
+    }
     const int sm = slot_of(zm), sc = slot_of(pc), sp = slot_of(zp);
     TbNb n;
     n.cA = tb_row6(tile_row(sc, rm), lane); n.cB = tb_row6(tile_row(sc, r), lane); n.cC = tb_row6(tile_row(sc, rp), lane);
@@ -1325,8 +1385,9 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs_tb(Geom g, const uint
 
   const int t_end = z1 - 1 + 2 * (S - 1);
   for (int t = z0; t <= t_end; ++t) {
-    if (!uzero && t + 2 <= zmax_load) load_plane(t + 2);
-    if (pfd > 0 && valid && pfa && t + pfd < z1) {
+    if (!uzero && t + 2 + (STAGE ? 1 : 0) <= zmax_load) load_plane(t + 2 + (STAGE ? 1 : 0));
+    if (STAGE) { stage_plane(t + 2); cp_async_commit(); }
+    if (!STAGE && pfd > 0 && valid && pfa && t + pfd < z1) {
       const char* q = pfa + pf_stride * (t + pfd);
       if (lane >= 4) { mad_prefetch_l2(q); mad_prefetch_l2(q + pf_row); }
     }
@@ -1343,7 +1404,8 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs_tb(Geom g, const uint
       const int pc = t - 2 * s;
       if (valid && pc >= z0 && pc < z1) relax(s, pc, rb, ya + 1, ra, rp_b);
     }
-    cp_async_wait_all();
+    if (STAGE) cp_async_wait_group<1>();  // everything but this step's group: the operands and the u plane of step t + 1 are in
+    else cp_async_wait_all();
     __syncthreads();
   }
 }

@@ -144,7 +144,8 @@ struct madgpu_ctx {
   int gs_coef16;    // fused Gauss-Seidel reads pre-evaluated fp16 operator rows (default) instead of the tensor planes
   int gs_fused;     // 3-D Gauss-Seidel as one fused pass per sweep (default) instead of one pass per colour
   int fast_cfg;     // CTA shape / register cap of the streaming kernels (tuning hook)
-  int res64_smem;   // MADGPU_RES64_SMEM: 0 = all-register fp64 residual (k_fast_sweep<MODE_RES_C32>), 3 / 4 = k_fast_res64 capped for 3 / 4 CTAs per SM
+  int res64_smem;   // MADGPU_RES64_SMEM: 0 (default) = all-register fp64 residual (k_fast_sweep<MODE_RES_C32>), 3 / 4 = k_fast_res64 capped for 3 / 4 CTAs per SM
+                    // (measured on B200 at 512^3: 1.66 ms all-register, 2.16 / 3.44 ms with the shared-memory ring -- kept as an A/B hook)
   int res64_minb;   // MADGPU_RES64_MINB=3: register cap of the fp64 residual for 3 CTAs per SM
   int res64_c32;    // level-0 fp64 residual with the operator row evaluated in fp32 -- the row the fp32 sweeps relax -- and applied in fp64 (default; MADGPU_RES64_COEF32=0: fp64 row)
   int fast_min_nx;  // 3-D levels with nx >= this use the streaming kernels of mad_fast.cuh
@@ -562,16 +563,18 @@ void op_zero(madgpu_ctx* ctx, Level& L, float* p)
 }
 
 // ---- temporal blocking of the Gauss-Seidel sweeps (fast::k_coef_gs_tb) -----------------------------------------------------
-constexpr int TB_WP = 8;  // warps (row pairs) per CTA: tiles of 128 x 16 voxels
+// warps (row pairs) per CTA: tiles of 128 x 16 voxels; the staged single-sweep variant (MADGPU_GS_TB_SINGLE=2) uses 128 x 8 so that
+// two CTAs fit the shared memory of an SM
+int tb_wp(const madgpu_ctx* ctx) { return ctx->gs_tb_single == 2 ? 4 : 8; }
 bool use_tb(const madgpu_ctx* ctx, const Level& L)
 {
   return (ctx->gs_tb > 1 || ctx->gs_tb_single) && ctx->gs_fused && ctx->gs_coef16 && !L.coef16_off && use_fast(ctx, L) && gs_pairs(ctx, L) && L.g.ny >= 8 && L.g.nz >= 8;
 }
 // planes per CTA: ~4 waves of the two resident CTAs per SM; long chunks keep the fill / drain steps of the sweep pipeline (2 per
 // fused sweep) and the frozen z faces rare
-int tb_zc(const Geom& g)
+int tb_zc(const Geom& g, int wp)
 {
-  const long long cxy = (long long)((g.nx + fast::TX - 1) / fast::TX) * ((g.ny + 2 * TB_WP - 1) / (2 * TB_WP));
+  const long long cxy = (long long)((g.nx + fast::TX - 1) / fast::TX) * ((g.ny + 2 * wp - 1) / (2 * wp));
   const long long chunks = std::max(1ll, (148ll * 2 * 4) / std::max(1ll, cxy));
   int zc = (int)std::max(16ll, (g.nz + chunks - 1) / chunks);
   zc = (zc + 1) & ~1;
@@ -580,16 +583,16 @@ int tb_zc(const Geom& g)
 // sweeps fused by the next pass when `remaining` sweeps of the leg are left
 int tb_fuse(const madgpu_ctx* ctx, int remaining) { return std::min(remaining >= 3 ? 3 : remaining, ctx->gs_tb); }
 
-template <int S>
+template <int S, int WP, int MINB, bool STAGE>
 void launch_tb(madgpu_ctx* ctx, Level& L, const Geom& gg, int uz)
 {
   static bool attr_set = false;  // per instantiation; the attribute is a property of the function
-  const size_t smem = fast::tb_smem_bytes(S, TB_WP);
-  if (!attr_set) { cudaFuncSetAttribute(fast::k_coef_gs_tb<S, TB_WP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  const int zc = tb_zc(L.g);
-  const int oy = L.tb_flip ? TB_WP : 0, oz = L.tb_flip ? zc / 2 : 0;
-  const dim3 grid((L.g.nx + fast::TX - 1) / fast::TX, (L.g.ny + oy + 2 * TB_WP - 1) / (2 * TB_WP), (L.g.nz + oz + zc - 1) / zc);
-  MAD_LAUNCH((fast::k_coef_gs_tb<S, TB_WP, 2>), grid, dim3(32, TB_WP), smem, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, oy, oz, ctx->pf_dist, uz);
+  const size_t smem = fast::tb_smem_bytes(S, WP) + (STAGE ? fast::tb_stage_bytes(WP) : 0);
+  if (!attr_set) { cudaFuncSetAttribute(fast::k_coef_gs_tb<S, WP, MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  const int zc = tb_zc(L.g, WP);
+  const int oy = L.tb_flip ? WP : 0, oz = L.tb_flip ? zc / 2 : 0;
+  const dim3 grid((L.g.nx + fast::TX - 1) / fast::TX, (L.g.ny + oy + 2 * WP - 1) / (2 * WP), (L.g.nz + oz + zc - 1) / zc);
+  MAD_LAUNCH((fast::k_coef_gs_tb<S, WP, MINB, STAGE>), grid, dim3(32, WP), smem, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, oy, oz, ctx->pf_dist, uz);
   L.tb_flip ^= 1;
 }
 
@@ -660,9 +663,11 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       Scope s(ctx, cls);
       const int fuse = use_tb(ctx, L) ? tb_fuse(ctx, n_iter - it) : 0;
       if (fuse >= 1) {  // `fuse` sweeps of this leg in one pass over shared-memory plane rings (temporal blocking; 1: MADGPU_GS_TB_SINGLE)
-        if (fuse == 3) launch_tb<3>(ctx, L, gg, uz);
-        else if (fuse == 2) launch_tb<2>(ctx, L, gg, uz);
-        else launch_tb<1>(ctx, L, gg, uz);
+        if (fuse == 3) launch_tb<3, 8, 2, false>(ctx, L, gg, uz);
+        else if (fuse == 2) launch_tb<2, 8, 2, false>(ctx, L, gg, uz);
+        else if (ctx->gs_tb_single == 2) launch_tb<1, 4, 2, true>(ctx, L, gg, uz);   // operands staged by cp.async, tiles of 128 x 8, two CTAs per SM
+        else if (ctx->gs_tb_single == 3) launch_tb<1, 8, 1, true>(ctx, L, gg, uz);   // the same on tiles of 128 x 16, one CTA per SM
+        else launch_tb<1, 8, 2, false>(ctx, L, gg, uz);
         it += fuse - 1;
       } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
         const int zc = fast_zc(L.g, 8);
@@ -1720,7 +1725,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     e = getenv("MADGPU_RES64_COEF32");
     ctx->res64_c32 = e ? atoi(e) : 1;
     e = getenv("MADGPU_RES64_SMEM");
-    ctx->res64_smem = e ? atoi(e) : 3;
+    ctx->res64_smem = e ? atoi(e) : 0;
     e = getenv("MADGPU_RES64_MINB");
     ctx->res64_minb = e ? atoi(e) : 2;
     e = getenv("MADGPU_FAST_CFG");
@@ -2124,8 +2129,8 @@ int madgpu_gs_leg_plan(const madgpu_ctx* ctx, int32_t level, int32_t n_iter, int
     const bool tb_ok = ctx->p.smoother == MADGPU_SMOOTHER_GS && use_tb(ctx, L);
     const int fuse = tb_ok ? tb_fuse(ctx, n_iter - it) : 1;
     if (tb_ok) {
-      const int zc = tb_zc(L.g);
-      q[0] = fuse; q[1] = fast::TX; q[2] = 2 * TB_WP; q[3] = zc; q[4] = flip ? TB_WP : 0; q[5] = flip ? zc / 2 : 0;
+      const int wp = tb_wp(ctx), zc = tb_zc(L.g, wp);
+      q[0] = fuse; q[1] = fast::TX; q[2] = 2 * wp; q[3] = zc; q[4] = flip ? wp : 0; q[5] = flip ? zc / 2 : 0;
       flip ^= 1;
     } else {
       q[0] = 1; q[1] = tile[0]; q[2] = tile[1]; q[3] = tile[2]; q[4] = 0; q[5] = 0;
