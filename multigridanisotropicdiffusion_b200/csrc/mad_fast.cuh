@@ -1056,11 +1056,13 @@ __device__ __forceinline__ float offdiag16_rows(const CoefRaw& c, const URows4& 
   return s;
 }
 
-template <int WP, int MINB>
+// PRIVATE: the tile is the warp's own row pair (128 x 2 x zc): the rows above and below always carry the previous sweep's values, so
+// the warps of a CTA never exchange anything and the two CTA-wide barriers per plane step are gone (MADGPU_GS_PRIVATE).
+template <int WP, int MINB, bool PRIVATE = false>
 __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
                                                               const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero)
 {
-  __shared__ float4 sh[2][2 * WP][32];
+  __shared__ float4 sh[PRIVATE ? 1 : 2][PRIVATE ? 1 : 2 * WP][32];
   const int lane = threadIdx.x, w = threadIdx.y;
   Pos p;
   p.lane = lane;
@@ -1077,7 +1079,8 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
   // image rows behind the four slots (node mirror at the y ends) and the tile rows that publish their new values
   const int rA = yb == 0 ? 1 : yb - 1, rD = yb + 2 >= g.ny ? g.ny - 2 : yb + 2;
   const int tA = rA - ytile, tD = rD - ytile;
-  const bool has_A = tA >= 0 && tA < 2 * WP, has_D = tD >= 0 && tD < 2 * WP;
+  // PRIVATE: only the node mirrors at the two y ends point back into the warp's own pair (row -1 is row 1, row ny is row ny - 2)
+  const bool has_A = PRIVATE ? rA == yb + 1 : (tA >= 0 && tA < 2 * WP), has_D = PRIVATE ? rD == yb : (tD >= 0 && tD < 2 * WP);
   const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
   const int xo = p.xl;
   const int oA = rA * g.pitch + xo, oB = yb * g.pitch + xo, oC = (yb + 1) * g.pitch + xo, oD = rD * g.pitch + xo;
@@ -1111,8 +1114,13 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
     const V4<float> fB = finish4<float>(rfB), fC = finish4<float>(rfC);
     // plane z-1 was relaxed one step ago: the neighbouring warps' rows come from the tile's row buffer
     if (z > z0) {
-      if (has_A) { const float4 q = sh[pb][tA][lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
-      if (has_D) { const float4 q = sh[pb][tD][lane]; um.r[3].v[1] = q.x; um.r[3].v[2] = q.y; um.r[3].v[3] = q.z; um.r[3].v[4] = q.w; }
+      if constexpr (PRIVATE) {  // the mirrored rows are the warp's own: their new values of plane z-1 are in registers
+        if (has_A) um.r[0] = um.r[2];
+        if (has_D) um.r[3] = um.r[1];
+      } else {
+        if (has_A) { const float4 q = sh[pb][tA][lane]; um.r[0].v[1] = q.x; um.r[0].v[2] = q.y; um.r[0].v[3] = q.z; um.r[0].v[4] = q.w; }
+        if (has_D) { const float4 q = sh[pb][tD][lane]; um.r[3].v[1] = q.x; um.r[3].v[2] = q.y; um.r[3].v[3] = q.z; um.r[3].v[4] = q.w; }
+      }
     }
     if (z == g.nz - 1 && g.zhi_phys) up = um;  // mirrored plane z+1 == plane z-1, already relaxed
     // relax one of the warp's two rows: even x, then odd x (x-neighbours through shuffles)
@@ -1133,16 +1141,18 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
         if (lane > 0) uc.r[row].v[0] = l;
         if (p.xb) mirror_x(uc.r[row], p.xt, p.jl);
       }
-      sh[cb][2 * w + row - 1][lane] = make_float4(n0, n1, n2, n3);
+      if constexpr (!PRIVATE) sh[cb][2 * w + row - 1][lane] = make_float4(n0, n1, n2, n3);
       const float res[4] = {n0, n1, n2, n3};
       if (p.xt < g.nx) { store4<float>(out, zb + orow, p.xt, g.nx, res); store_ghosts<float>(g, z, orow, p.xt, res); }
     };
     // phase 1: even rows (rows y0-1 and y0+1 of this plane still hold the previous sweep)
     if (valid) relax(1, cB, fB, oB);
-    __syncthreads();
+    if constexpr (!PRIVATE) __syncthreads();
     // phase 2: odd rows; row y0+2 (an even row) was relaxed in phase 1 by the next warp
     if (valid) {
-      if (has_D) {
+      if constexpr (PRIVATE) {
+        if (has_D) uc.r[3] = uc.r[1];  // top row pair: the mirrored row y0+2 is row y0, just relaxed
+      } else if (has_D) {
         const float* sd = reinterpret_cast<const float*>(&sh[cb][tD][0]);
         const float4 q = reinterpret_cast<const float4*>(sd)[lane];
         uc.r[3].v[1] = q.x; uc.r[3].v[2] = q.y; uc.r[3].v[3] = q.z; uc.r[3].v[4] = q.w;
@@ -1152,7 +1162,7 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
       }
       relax(2, cC, fC, oC);
     }
-    __syncthreads();
+    if constexpr (!PRIVATE) __syncthreads();
     um = uc; uc = up;
   }
 }

@@ -163,6 +163,7 @@ struct madgpu_ctx {
   };
   std::vector<CycleGraph> graphs;
   long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
+  int gs_private;          // MADGPU_GS_PRIVATE=1: the row-pair sweep with warp-private tiles (128 x 2 x zc), no CTA barriers
   int gs_tb_single;        // MADGPU_GS_TB_SINGLE=1: every sweep through k_coef_gs_tb<1> (shared-memory ring fed by cp.async, tiles of 128 x 16) instead of k_coef_gs2: A/B hook
   int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB = 2 or 3; default 1 = off:
                            // measured on B200 at 512^3 a fused pass of 3 sweeps takes 2.04 ms against 3 x 0.77 ms -- the packed rows of the older planes
@@ -669,9 +670,10 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
         else if (ctx->gs_tb_single == 3) launch_tb<1, 8, 1, true>(ctx, L, gg, uz);   // the same on tiles of 128 x 16, one CTA per SM
         else launch_tb<1, 8, 2, false>(ctx, L, gg, uz);
         it += fuse - 1;
-      } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc
+      } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc (128 x 2 x zc with MADGPU_GS_PRIVATE: no barriers)
         const int zc = fast_zc(L.g, 8);
-        MAD_LAUNCH((fast::k_coef_gs2<4, 3>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        if (ctx->gs_private) MAD_LAUNCH((fast::k_coef_gs2<4, 3, true>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        else MAD_LAUNCH((fast::k_coef_gs2<4, 3, false>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
         const int zc = fast_zc(L.g, 4);
         MAD_LAUNCH((fast::k_coef_gs<4, 4>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
@@ -1739,6 +1741,8 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     ctx->restrict_cell = e ? atoi(e) : 1;
     e = getenv("MADGPU_GS_TB");
     ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 1;
+    e = getenv("MADGPU_GS_PRIVATE");
+    ctx->gs_private = e ? atoi(e) : 0;
     e = getenv("MADGPU_GS_TB_SINGLE");
     ctx->gs_tb_single = e ? atoi(e) : 0;
     e = getenv("MADGPU_COARSE_HOST");
@@ -2145,8 +2149,8 @@ int madgpu_gs_tile(const madgpu_ctx* ctx, int32_t level, int32_t tile[3])
   if (!ctx || !tile || level < 0 || level >= ctx->nlevels) return MADGPU_EINVAL;
   const Level& L = ctx->lv[level];
   if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast(ctx, L) && ctx->gs_fused) {
-    const int wy = (ctx->gs_coef16 && !L.coef16_off) ? (gs_pairs(ctx, L) ? 8 : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
-    tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy);
+    const int wy = (ctx->gs_coef16 && !L.coef16_off) ? (gs_pairs(ctx, L) ? (ctx->gs_private ? 2 : 8) : 4) : (ctx->fast_cfg == 1 || ctx->fast_cfg == 5 || ctx->fast_cfg == 8) ? 8 : ctx->fast_cfg == 6 ? 2 : 4;
+    tile[0] = fast::TX; tile[1] = wy; tile[2] = fast_zc(L.g, wy == 2 ? 8 : wy);  // the warp-private variant keeps the launch geometry of the row-pair kernel
   } else if (ctx->p.smoother == MADGPU_SMOOTHER_GS && use_fast2_gs(ctx, L)) {
     tile[0] = fast::TX; tile[1] = fast2_yc(L.g); tile[2] = 1;  // 2-D ordering: rows in y order, even then odd columns (mad_fast2d.cuh)
   } else {
