@@ -1057,7 +1057,9 @@ __device__ __forceinline__ float offdiag16_rows(const CoefRaw& c, const URows4& 
 }
 
 // PRIVATE: the tile is the warp's own row pair (128 x 2 x zc): the rows above and below always carry the previous sweep's values, so
-// the warps of a CTA never exchange anything and the two CTA-wide barriers per plane step are gone (MADGPU_GS_PRIVATE).
+// the warps of a CTA never exchange anything and the two CTA-wide barriers per plane step are gone (MADGPU_GS_PRIVATE=1).  Measured
+// on B200 at 512^3: 0.731 instead of 0.769 ms per sweep, but the four-times-denser tile faces cost one V-cycle in 23 to relres 1e-10
+// (6,6,6,6 instead of 6,6,6,5), so the time of a whole solve does not improve (0.306 against 0.302 s): opt-in, not the default.
 template <int WP, int MINB, bool PRIVATE = false>
 __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
                                                               const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero)
@@ -1191,7 +1193,9 @@ constexpr int TB_ROWF = 136;  // floats per tile row: [3] = x0-1, [4..131] = the
 __host__ __device__ constexpr int tb_planes(int S) { return 2 * S + 2; }
 __host__ __device__ constexpr size_t tb_smem_bytes(int S, int WP) { return (size_t)tb_planes(S) * (2 * WP + 2) * TB_ROWF * sizeof(float); }
 // STAGE (single sweeps only): the packed rows and f of the planes t, t+1, t+2 are staged in shared memory as well, by cp.async two
-// planes ahead of their use -- loads in flight without a register destination, which is what the register-bound k_coef_gs2 lacks
+// planes ahead of their use -- loads in flight without a register destination, which is what the register-bound k_coef_gs2 lacks.
+// Measured on B200 at 512^3 (MADGPU_GS_TB_SINGLE=2|3): 1.37 ms per sweep against 0.77 -- every operand now crosses shared memory
+// twice and the sweep is bound by its load / store unit.  Kept as a tested A/B hook.
 constexpr int TB_STAGE_DEPTH = 3;
 __host__ __device__ constexpr size_t tb_stage_bytes(int WP)  // + one more plane of the u ring
 {

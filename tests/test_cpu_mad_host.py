@@ -83,7 +83,7 @@ def test_packed_rows_with_a_large_diagonal(MadSolver, monkeypatch):
         s.set_tensor(T)
         out = s.solve(img, out_dtype=np.float64)
         st = s.last_stats
-        assert s.gs_tile(0)[1] == 8  # the row-pair packed sweep (128 x 8 tiles)
+        assert s.gs_tile(0)[1] in (2, 8)  # the row-pair packed sweep (tiles of 128 x 8, or 128 x 2 with warp-private tiles)
     o = O.Oracle(shape, sp, T.astype(np.float64), 0.1, smoother=0, nu=3)
     ref, cyc, _ = o.solve(img.astype(np.float64), tolerance=1e-8, max_cycles=60)
     assert np.isfinite(out).all() and st["final_relres"][0] <= 1e-8

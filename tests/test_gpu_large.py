@@ -116,7 +116,7 @@ def test_operators_on_512_wide_planes():
     with MadSolver(shape, phantom.VED_SPACING, time_step=DT, smoother=MadSolver.GS, iterations_per_grid=NU) as s:
         s.set_tensor(T)
         tile = s.gs_tile(0)
-        assert tile is not None and tile[0] == 128 and tile[1] == 8
+        assert tile is not None and tile[0] == 128 and tile[1] in (2, 8)
         plan = s.gs_leg_plan(0, 2)
         g = s.op_smooth(0, u, f, smoother=0, n_iter=2)
         S = o.stencil(0)
