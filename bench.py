@@ -478,8 +478,10 @@ def run_ours(args):
     sweeps = 2 * nu * args.steps
     achieved = ALG_BYTES_SWEEP_3D * nvox * sweeps / (sm_ms * 1e-3) / 1e9 if sm_ms > 0 else None
     tile = s.gs_tile(0) if args.smoother == "gs" else None
+    tb_env = int(os.environ.get("MADGPU_GS_TB", "1") or 1) > 1 or int(os.environ.get("MADGPU_GS_TB_SINGLE", "0") or 0) > 0
     launched_kernel = ("k_fast_sweep<MODE_WJ>" if args.smoother == "wj" else
-                       "k_coef_gs2" if tile and tile[1] == 8 else "k_coef_gs" if tile else "k_gs_color")
+                       "k_coef_gs_tb" if tile and tb_env else  # opt-in shared-memory sweeps
+                       "k_coef_gs2" if tile and tile[1] == 8 else "k_coef_gs2_private" if tile and tile[1] == 2 else "k_coef_gs" if tile else "k_gs_color")
     traffic, traffic_src = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
@@ -578,9 +580,22 @@ def run_ours(args):
             barrier()
             one = extra_volume_run((512, 512, 512), args, smoother, 0, 1, local_rank, dev, False, lambda: torch.cuda.synchronize(), active=rank == 0)
             barrier()
+            big = None
+            if world == 8 and not args.no_n1_1024:
+                # the same 1024^3 volume on ONE GPU of this box (it fits: ~80 GB): the strong-scaling denominator of configs[4]
+                try:
+                    big = extra_volume_run(wshape, args, smoother, 0, 1, local_rank, dev, False, lambda: torch.cuda.synchronize(), active=rank == 0)
+                except Exception as e:  # noqa: BLE001 -- e.g. out of memory on a box whose GPU 0 is shared
+                    big = {"error": f"{type(e).__name__}: {e}"}
+                torch.cuda.empty_cache()
+                barrier()
             if rank == 0:
                 w["vs_n1"] = w["value"] / one["value"]
                 w["n1_same_run"] = one
+                if big is not None:
+                    w["n1_same_volume"] = big
+                    if big.get("value"):
+                        w["vs_n1_same_volume"] = w["value"] / big["value"]
                 w["target"] = "BASELINE.json north_star: >= 6x one GPU at 512^3 for 1024^3 on 8 GPUs (same work per GPU)"
             extra = {"weak_1024" if world == 8 else f"weak_512x512x{512 * world}": w}
         except Exception as e:  # noqa: BLE001
@@ -636,6 +651,7 @@ def main():
     ap.add_argument("--no-ved", dest="ved", action="store_false")
     ap.add_argument("--no-slab-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU parity solves after the timed region")
     ap.add_argument("--weak", action="store_true", help="N > 1: also run the weak-scaling volume (512 x 512 x 512N; 1024^3 at N = 8 is always run)")
+    ap.add_argument("--no-n1-1024", action="store_true", help="N = 8: skip the one-GPU run of the 1024^3 volume (the strong-scaling denominator)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent volumes per GPU instead of z-slabs of one volume")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
