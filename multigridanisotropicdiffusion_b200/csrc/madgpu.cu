@@ -672,6 +672,7 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
         it += fuse - 1;
       } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc (128 x 2 x zc with MADGPU_GS_PRIVATE: no barriers)
         const int zc = fast_zc(L.g, 8);
+        // (capped at 128 registers for 16 warps per SM both variants spill and take 0.89 instead of 0.77 / 0.73 ms: profiles/r02o_*)
         if (ctx->gs_private) MAD_LAUNCH((fast::k_coef_gs2<4, 3, true>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
         else MAD_LAUNCH((fast::k_coef_gs2<4, 3, false>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
       } else {
