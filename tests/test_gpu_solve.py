@@ -212,3 +212,28 @@ def test_single_level_and_zero_rhs():
     assert s.last_stats["cycles_per_step"] == [1]
     assert np.all(z == 0)
     s.close()
+
+
+@pytest.mark.parametrize("smoother", ["gs", "wj"])
+def test_a_context_survives_new_tensors(smoother):
+    """SetDiffusionTensor on a live context (VED.hxx:381-402 calls it once per outer iteration): the packed rows are rebuilt, the captured
+    coarse-level cycle and the captured Gauss-Jordan elimination are replayed on the new operator.  Tensor A, B, A again on one context:
+    the third solve repeats the first bit for bit, the second equals a fresh context's."""
+    from multigridanisotropicdiffusion_b200 import MadSolver
+    shape, sp = (40, 48, 136), (0.3125, 0.3125, 0.5)
+    sm = MadSolver.GS if smoother == "gs" else MadSolver.WJ
+    TA, TB = random_spd_tensor(shape, seed=11), random_spd_tensor(shape, seed=12)
+    img = random_image(shape, seed=13)
+    kw = dict(time_step=0.1, smoother=sm, iterations_per_grid=3, tolerance=1e-9, max_cycles=60, number_of_steps=2)
+    with MadSolver(shape, sp, **kw) as s:
+        outs = []
+        for T in (TA, TB, TA):
+            s.set_tensor(T)
+            outs.append(s.solve(img, out_dtype=np.float64))
+            assert max(s.last_stats["final_relres"]) <= 1e-9
+    with MadSolver(shape, sp, **kw) as s:
+        s.set_tensor(TB)
+        fresh = s.solve(img, out_dtype=np.float64)
+    assert np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[1], fresh)
+    assert rel_l2(outs[0], outs[1]) > 1e-4
