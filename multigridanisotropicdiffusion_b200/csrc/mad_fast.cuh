@@ -1062,8 +1062,11 @@ __device__ __forceinline__ float offdiag16_rows(const CoefRaw& c, const URows4& 
 // (6,6,6,6 instead of 6,6,6,5), so the time of a whole solve does not improve (0.306 against 0.302 s): opt-in, not the default.
 template <int WP, int MINB, bool PRIVATE = false>
 __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
-                                                              const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero)
+                                                              const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero,
+                                                              int yshift = 0)
 {
+  // yshift (PRIVATE only, 0 or 1): the row pairs start at odd rows -- (-1, 0), (1, 2), ..., (ny-1, ny), the two end pairs holding one
+  // image row each -- so that a host which alternates it between sweeps moves the tile faces (MADGPU_GS_PRIVATE=2)
   __shared__ float4 sh[PRIVATE ? 1 : 2][PRIVATE ? 1 : 2 * WP][32];
   const int lane = threadIdx.x, w = threadIdx.y;
   Pos p;
@@ -1075,17 +1078,21 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
   p.dh = (lane == 0 ? max(p.xt - 1, 0) : min(p.xt + 4, g.nx - 1)) - p.xl;
   p.xb = p.xt == 0 || (p.jl >= 0 && p.jl < 4);
   const int ytile = blockIdx.y * 2 * WP;
-  const int y0 = ytile + 2 * w;           // even row of this warp; ny is even, so y0 + 1 exists whenever y0 does
-  const bool valid = y0 < g.ny;
-  const int yb = valid ? y0 : 0;
-  // image rows behind the four slots (node mirror at the y ends) and the tile rows that publish their new values
-  const int rA = yb == 0 ? 1 : yb - 1, rD = yb + 2 >= g.ny ? g.ny - 2 : yb + 2;
-  const int tA = rA - ytile, tD = rD - ytile;
-  // PRIVATE: only the node mirrors at the two y ends point back into the warp's own pair (row -1 is row 1, row ny is row ny - 2)
-  const bool has_A = PRIVATE ? rA == yb + 1 : (tA >= 0 && tA < 2 * WP), has_D = PRIVATE ? rD == yb : (tD >= 0 && tD < 2 * WP);
+  const int y0 = ytile + 2 * w - (PRIVATE ? yshift : 0);  // first row of this warp's pair; ny is even
+  // which of the pair's two rows exist (both, except in the two end pairs of a shifted grid)
+  const bool relaxB = y0 >= 0 && y0 < g.ny, relaxC = y0 + 1 >= 0 && y0 + 1 < g.ny;
+  const bool valid = relaxB || relaxC;
+  // image rows behind the four slots: node mirror at the y ends (row -1 is row 1, row ny is row ny - 2)
+  auto mir = [&](int y) { return !valid ? 0 : (y < 0 ? -y : (y >= g.ny ? 2 * (g.ny - 1) - y : y)); };
+  const int rA = mir(y0 - 1), rB = mir(y0), rC = mir(y0 + 1), rD = mir(y0 + 2);
+  const int tA = rA - ytile, tD = rD - ytile;  // tile rows that publish the new values of rows A and D (shared tiles)
+  // PRIVATE: only the node mirrors at the two y ends point back into the warp's own pair
+  const bool has_A = PRIVATE ? (relaxB && relaxC && y0 == 0) : (tA >= 0 && tA < 2 * WP);
+  const bool has_D = PRIVATE ? (relaxB && relaxC && y0 + 2 == g.ny) : (tD >= 0 && tD < 2 * WP);
+  const bool c_first = PRIVATE && (y0 & 1);  // the even row of the pair is relaxed first (in a shifted grid that is row C)
   const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, g.nz);
   const int xo = p.xl;
-  const int oA = rA * g.pitch + xo, oB = yb * g.pitch + xo, oC = (yb + 1) * g.pitch + xo, oD = rD * g.pitch + xo;
+  const int oA = rA * g.pitch + xo, oB = rB * g.pitch + xo, oC = rC * g.pitch + xo, oD = rD * g.pitch + xo;
   URows4 um, uc, up;
   auto zero_rows = [](URows4& R) {
 #pragma unroll
@@ -1109,7 +1116,7 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
     const int cb = z & 1, pb = cb ^ 1;
     const int zb = z * (int)g.plane;
     // ---- loads of this plane step ----
-    const CoefRaw cB = issue_coef(coef, g, p, yb, z), cC = issue_coef(coef, g, p, yb + 1, z);
+    const CoefRaw cB = issue_coef(coef, g, p, rB, z), cC = issue_coef(coef, g, p, rC, z);
     const Raw4<float> rfB = issue4(f, zb + oB), rfC = issue4(f, zb + oC);
     if (uzero) zero_rows(up);
     else load_rows(zmirror_hi(g, z), up);
@@ -1148,10 +1155,13 @@ __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4*
       if (p.xt < g.nx) { store4<float>(out, zb + orow, p.xt, g.nx, res); store_ghosts<float>(g, z, orow, p.xt, res); }
     };
     // phase 1: even rows (rows y0-1 and y0+1 of this plane still hold the previous sweep)
-    if (valid) relax(1, cB, fB, oB);
+    if (c_first) {  // shifted warp-private pair: row C is the even one
+      if (relaxC) relax(2, cC, fC, oC);
+      if (relaxB) relax(1, cB, fB, oB);
+    } else if (relaxB) relax(1, cB, fB, oB);
     if constexpr (!PRIVATE) __syncthreads();
     // phase 2: odd rows; row y0+2 (an even row) was relaxed in phase 1 by the next warp
-    if (valid) {
+    if (relaxC && !c_first) {
       if constexpr (PRIVATE) {
         if (has_D) uc.r[3] = uc.r[1];  // top row pair: the mirrored row y0+2 is row y0, just relaxed
       } else if (has_D) {

@@ -163,7 +163,8 @@ struct madgpu_ctx {
   };
   std::vector<CycleGraph> graphs;
   long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
-  int gs_private;          // MADGPU_GS_PRIVATE=1: the row-pair sweep with warp-private tiles (128 x 2 x zc), no CTA barriers
+  int gs_private;          // MADGPU_GS_PRIVATE=1: the row-pair sweep with warp-private tiles (128 x 2 x zc), no CTA barriers; 2: the same on a
+                           // grid of pairs that alternates between even and odd first rows from sweep to sweep
   int gs_tb_single;        // MADGPU_GS_TB_SINGLE=1: every sweep through k_coef_gs_tb<1> (shared-memory ring fed by cp.async, tiles of 128 x 16) instead of k_coef_gs2: A/B hook
   int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB = 2 or 3; default 1 = off:
                            // measured on B200 at 512^3 a fused pass of 3 sweeps takes 2.04 ms against 3 x 0.77 ms -- the packed rows of the older planes
@@ -673,8 +674,15 @@ void op_smooth(madgpu_ctx* ctx, int l, int smoother, int n_iter, bool zero_first
       } else if (gs_pairs(ctx, L)) {  // one warp per row pair: tile 128 x 8 x zc (128 x 2 x zc with MADGPU_GS_PRIVATE: no barriers)
         const int zc = fast_zc(L.g, 8);
         // (capped at 128 registers for 16 warps per SM both variants spill and take 0.89 instead of 0.77 / 0.73 ms: profiles/r02o_*)
-        if (ctx->gs_private) MAD_LAUNCH((fast::k_coef_gs2<4, 3, true>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
-        else MAD_LAUNCH((fast::k_coef_gs2<4, 3, false>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
+        if (ctx->gs_private) {
+          // MADGPU_GS_PRIVATE=2: the pairs start at odd rows in every other sweep, so that the tile faces of one sweep lie inside the
+          // pairs of the next (the grid then has one more pair: (-1, 0) ... (ny-1, ny))
+          const int ysh = ctx->gs_private == 2 ? L.tb_flip : 0;
+          dim3 fg = fast_grid(L.g, 8, zc);
+          fg.y = (L.g.ny + ysh + 7) / 8;
+          MAD_LAUNCH((fast::k_coef_gs2<4, 3, true>), fg, dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz, ysh);
+          if (ctx->gs_private == 2) L.tb_flip ^= 1;
+        } else MAD_LAUNCH((fast::k_coef_gs2<4, 3, false>), fast_grid(L.g, 8, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz, 0);
       } else {
         const int zc = fast_zc(L.g, 4);
         MAD_LAUNCH((fast::k_coef_gs<4, 4>), fast_grid(L.g, 4, zc), dim3(32, 4), 0, ctx->stream, gg, L.coef16, L.u, L.f, L.tmp, zc, ctx->pf_dist, uz);
@@ -2138,7 +2146,9 @@ int madgpu_gs_leg_plan(const madgpu_ctx* ctx, int32_t level, int32_t n_iter, int
       q[0] = fuse; q[1] = fast::TX; q[2] = 2 * wp; q[3] = zc; q[4] = flip ? wp : 0; q[5] = flip ? zc / 2 : 0;
       flip ^= 1;
     } else {
-      q[0] = 1; q[1] = tile[0]; q[2] = tile[1]; q[3] = tile[2]; q[4] = 0; q[5] = 0;
+      const bool alt = ctx->gs_private == 2 && tile[1] == 2;  // warp-private pairs on an alternating grid
+      q[0] = 1; q[1] = tile[0]; q[2] = tile[1]; q[3] = tile[2]; q[4] = alt ? flip : 0; q[5] = 0;
+      if (alt) flip ^= 1;
     }
     it += fuse;
   }

@@ -146,8 +146,8 @@ GS_CASES = [
 ]
 
 
-@pytest.fixture(params=[(0, 0, 0, 1), (1, 0, 0, 1), (7, 0, 0, 1), (8, 0, 0, 1), (0, 1, 0, 1), (0, 1, 1, 1), (0, 1, 1, 3), (0, 1, 1, 0), (0, 1, 1, -2), (0, 1, 1, -3), (0, 1, 2, 1)],
-                ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}{'-pairs' if c[2] == 1 else '-private' if c[2] == 2 else ''}{'-tb3' if c[3] == 3 else '-tbsingle' if c[3] == 0 else '-staged' + str(-c[3]) if c[3] < 0 else ''}")
+@pytest.fixture(params=[(0, 0, 0, 1), (1, 0, 0, 1), (7, 0, 0, 1), (8, 0, 0, 1), (0, 1, 0, 1), (0, 1, 1, 1), (0, 1, 1, 3), (0, 1, 1, 0), (0, 1, 1, -2), (0, 1, 1, -3), (0, 1, 2, 1), (0, 1, 3, 1)],
+                ids=lambda c: f"cfg{c[0]}-rows{'16' if c[1] else '32'}{'-pairs' if c[2] == 1 else '-private' if c[2] == 2 else '-privalt' if c[2] == 3 else ''}{'-tb3' if c[3] == 3 else '-tbsingle' if c[3] == 0 else '-staged' + str(-c[3]) if c[3] < 0 else ''}")
 def gs_env(request, monkeypatch):
     """(kernel variant, packed fp16 operator rows, one warp per row pair, sweeps fused per pass): the default is (0, 1, 1, 1); the
     exact-row variants pin the ordering to fp32 rounding; the last one is the opt-in temporal blocking (MADGPU_GS_TB=3)."""
@@ -158,7 +158,7 @@ def gs_env(request, monkeypatch):
     monkeypatch.setenv("MADGPU_FAST_CFG", str(request.param[0]))
     monkeypatch.setenv("MADGPU_GS_COEF16", str(request.param[1]))
     monkeypatch.setenv("MADGPU_GS_PAIRS", str(min(request.param[2], 1)))
-    monkeypatch.setenv("MADGPU_GS_PRIVATE", "1" if request.param[2] == 2 else "0")  # warp-private tiles of the row-pair kernel
+    monkeypatch.setenv("MADGPU_GS_PRIVATE", str(max(request.param[2] - 1, 0)))  # warp-private tiles of the row-pair kernel (2: alternating grid)
     return request.param
 
 
