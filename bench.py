@@ -481,14 +481,14 @@ def run_ours(args):
     tb_env = int(os.environ.get("MADGPU_GS_TB", "1") or 1) > 1 or int(os.environ.get("MADGPU_GS_TB_SINGLE", "0") or 0) > 0
     launched_kernel = ("k_fast_sweep<MODE_WJ>" if args.smoother == "wj" else
                        "k_coef_gs_tb" if tile and tb_env else  # opt-in shared-memory sweeps
-                       "k_coef_gs2" if tile and tile[1] == 8 else "k_coef_gs2_private" if tile and tile[1] == 2 else "k_coef_gs" if tile else "k_gs_color")
+                       "k_coef_gs2<4,3,PRIVATE>" if tile and tile[1] == 2 else "k_coef_gs2<4,3>" if tile and tile[1] == 8 else "k_coef_gs" if tile else "k_gs_color")
     traffic, traffic_src = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        for key in ("smooth0", "smooth0_" + args.smoother):
+        for key in ("smooth0", "smooth0_shared_tiles", "smooth0_" + args.smoother):
             ent = prof.get(key, {})
             # only a capture of the kernel that was actually launched, at this size, counts
-            if ent.get("size") == n and ent.get("smoother") == args.smoother and world == 1 and ent.get("kernel", "").split("<")[0] == launched_kernel.split("<")[0]:
+            if ent.get("size") == n and ent.get("smoother") == args.smoother and world == 1 and ent.get("kernel", "") == launched_kernel:
                 traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
     except Exception:
         pass

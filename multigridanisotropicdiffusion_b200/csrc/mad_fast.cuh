@@ -1057,9 +1057,10 @@ __device__ __forceinline__ float offdiag16_rows(const CoefRaw& c, const URows4& 
 }
 
 // PRIVATE: the tile is the warp's own row pair (128 x 2 x zc): the rows above and below always carry the previous sweep's values, so
-// the warps of a CTA never exchange anything and the two CTA-wide barriers per plane step are gone (MADGPU_GS_PRIVATE=1).  Measured
-// on B200 at 512^3: 0.731 instead of 0.769 ms per sweep, but the four-times-denser tile faces cost one V-cycle in 23 to relres 1e-10
-// (6,6,6,6 instead of 6,6,6,5), so the time of a whole solve does not improve (0.306 against 0.302 s): opt-in, not the default.
+// the warps of a CTA never exchange anything and the two CTA-wide barriers per plane step are gone.  Measured on B200 at 512^3
+// (profiles/r02q_*): 0.68 instead of 0.78 ms per sweep -- 6.4 TB/s on the 32 B per voxel it moves, the rate of the barrier-free
+// residual kernel; the four-times-denser tile faces cost one V-cycle in 23 to relres 1e-10 (6,6,6,6 instead of 6,6,6,5), the whole
+// filter call still gets faster (0.297 against 0.305 s).  The default since then (MADGPU_GS_PRIVATE=2: alternating grid, see yshift).
 template <int WP, int MINB, bool PRIVATE = false>
 __global__ void __launch_bounds__(32 * WP, MINB) k_coef_gs2(Geom g, const uint4* __restrict__ coef, const float* __restrict__ u,
                                                               const float* __restrict__ f, float* __restrict__ out, int zc, int pfd, int uzero,

@@ -163,8 +163,9 @@ struct madgpu_ctx {
   };
   std::vector<CycleGraph> graphs;
   long long graph_voxels;  // MADGPU_GRAPH_VOXELS (0 = no graphs)
-  int gs_private;          // MADGPU_GS_PRIVATE=1: the row-pair sweep with warp-private tiles (128 x 2 x zc), no CTA barriers; 2: the same on a
-                           // grid of pairs that alternates between even and odd first rows from sweep to sweep
+  int gs_private;          // MADGPU_GS_PRIVATE: 2 (default) = the row-pair sweep with warp-private tiles (128 x 2 x zc, no CTA barriers) on a grid of
+                           // pairs that alternates between even and odd first rows from sweep to sweep; 1 = the same on a fixed grid; 0 = tiles of
+                           // 128 x 8 x zc shared by the four warps of a CTA (two barriers per plane step; the default until call q of round 2)
   int gs_tb_single;        // MADGPU_GS_TB_SINGLE=1: every sweep through k_coef_gs_tb<1> (shared-memory ring fed by cp.async, tiles of 128 x 16) instead of k_coef_gs2: A/B hook
   int gs_tb;               // temporal blocking of the Gauss-Seidel sweeps of a leg: up to this many sweeps per pass (MADGPU_GS_TB = 2 or 3; default 1 = off:
                            // measured on B200 at 512^3 a fused pass of 3 sweeps takes 2.04 ms against 3 x 0.77 ms -- the packed rows of the older planes
@@ -1751,7 +1752,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
     e = getenv("MADGPU_GS_TB");
     ctx->gs_tb = e ? std::min(std::max(atoi(e), 1), 3) : 1;
     e = getenv("MADGPU_GS_PRIVATE");
-    ctx->gs_private = e ? atoi(e) : 0;
+    ctx->gs_private = e ? atoi(e) : 2;
     e = getenv("MADGPU_GS_TB_SINGLE");
     ctx->gs_tb_single = e ? atoi(e) : 0;
     e = getenv("MADGPU_COARSE_HOST");
