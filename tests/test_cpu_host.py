@@ -171,3 +171,18 @@ def test_cmake_packaging_configures(tmp_path):
     if os.environ.get("MADGPU_TEST_CMAKE_BUILD") == "1":
         assert subprocess.run(["cmake", "--build", b, "-j", "4"], capture_output=True, text=True).returncode == 0
         assert os.path.exists(os.path.join(b, "libmadgpu.so"))
+
+
+def test_every_environment_hook_is_documented():
+    """INTEGRATION.md's table lists every MADGPU_* variable the library reads (csrc/*.cu), and nothing the library does not read."""
+    import re
+    csrc = os.path.join(ROOT, "multigridanisotropicdiffusion_b200", "csrc")
+    src = "".join(open(os.path.join(csrc, f)).read() for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h")))
+    read = set(re.findall(r'getenv\("(MADGPU_[A-Z0-9_]+)"\)', src))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    table = doc[doc.index("### Environment hooks"):]
+    documented = set(re.findall(r"`(MADGPU_[A-Z0-9_]+)`", table))
+    assert read - documented == set(), f"undocumented: {sorted(read - documented)}"
+    test_only = {"MADGPU_EMULATED_DEVICE", "MADGPU_FULL_EMULATION", "MADGPU_LARGE_TEST_DRYRUN", "MADGPU_PROPS_TEST_SIZE", "MADGPU_BENCH_PEER8",
+                 "MADGPU_ROOT", "MADGPU_REFERENCE"}
+    assert documented - read - test_only == set(), f"documented but never read: {sorted(documented - read - test_only)}"
