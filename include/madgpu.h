@@ -174,7 +174,9 @@ int madgpu_solve_u8(madgpu_ctx *ctx, const uint8_t *in, uint8_t *out, madgpu_sta
 int madgpu_solve_i16(madgpu_ctx *ctx, const int16_t *in, int16_t *out, madgpu_stats *stats);
 int madgpu_solve_f32(madgpu_ctx *ctx, const float *in, float *out, madgpu_stats *stats);
 int madgpu_solve_f64(madgpu_ctx *ctx, const double *in, double *out, madgpu_stats *stats);
-/* Same with DEVICE pointers to dense fp32 images (inputs already resident in HBM). */
+/* Same with DEVICE pointers to dense fp32 images (inputs already resident in HBM).  d_in == NULL continues from the fp64 result of
+ * the previous solve of this context instead of an fp32 image: the outer iterations of VEDMultigridImageFilter::GenerateData carry
+ * the image in double (itkVEDMultigridImageFilter.h:64, .hxx:105-123). */
 int madgpu_solve_device_f32(madgpu_ctx *ctx, const float *d_in, float *d_out, madgpu_stats *stats);
 
 /* Cycle-level driving of the same loop (benchmarks, per-V-cycle parity): begin stages the image and

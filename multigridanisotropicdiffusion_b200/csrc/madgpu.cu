@@ -92,6 +92,7 @@ struct madgpu_ctx {
   Level lv[MADGPU_MAX_LEVELS];
   double *u64, *f64;  // level-0 outer fields (plane-0 pointers)
   std::vector<void*> allocs;
+  bool have_result;  // run_steps has completed on this context: f64 holds its fp64 result
   double* Ainv;  // device, ncoarse^2
   double* gjM;   // device work matrix [A | I] of the Gauss-Jordan inverse (+ saved column, singular flag), kept between tensors
   int gj_n;
@@ -1501,6 +1502,7 @@ size_t pix_size(int t) { return t == MADGPU_PIX_U8 ? 1 : t == MADGPU_PIX_I16 ? 2
 
 int stage_input(madgpu_ctx* ctx, int type, const void* dev_dense)
 {
+  ctx->have_result = false;  // f64 is about to hold an image, not a result
   Level& L = ctx->lv[0];
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);
   switch (type) {
@@ -1583,6 +1585,7 @@ int run_steps(madgpu_ctx* ctx)
   ctx->st.solve_ms = solve_ms_total;
   CU(cudaGetLastError());
   if (!ctx->sticky.empty()) return fail(ctx, MADGPU_ECUDA, "%s", ctx->sticky.c_str());
+  ctx->have_result = P.number_of_steps > 0;  // f64 == u64 == the result (fp64)
   return 0;
 }
 
@@ -1706,6 +1709,7 @@ static int create_ctx(const madgpu_params* p, const void* nccl_id, cudaStream_t 
   ctx->dim = p->dim;
   ctx->ncomp = p->dim == 2 ? 3 : 6;
   ctx->Ainv = nullptr; ctx->ncoarse = 0; ctx->coarse_direct = false;
+  ctx->have_result = false;
   ctx->gjM = nullptr; ctx->gj_n = 0; ctx->gj_exec = nullptr; ctx->gj_graph_bad = false;
   ctx->partials = nullptr; ctx->d_scalar = nullptr; ctx->h_scalar = nullptr;
   ctx->tensor_set = false; ctx->profiling = 0; ctx->rhs_norm = 0; ctx->launches = 0;
@@ -1984,11 +1988,16 @@ int madgpu_solve_device_f32(madgpu_ctx* ctx, const float* d_in, float* d_out, ma
 {
   int rc = check_ready(ctx);
   if (rc) return rc;
-  if (!d_in || !d_out) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  if (!d_out) return fail(ctx, MADGPU_EINVAL, "null image pointer");
+  if (!d_in && !ctx->have_result) return fail(ctx, MADGPU_ESTATE, "d_in == NULL continues from the previous solve of this context, and there is none");
   CU(cudaSetDevice(ctx->p.device));
   begin_stats(ctx);
-  rc = stage_input(ctx, MADGPU_PIX_F32, d_in);
-  if (rc) return rc;
+  // d_in == NULL: the right-hand side is the fp64 result of the previous solve, which run_steps left in f64 (…Filter.hxx:248-261) --
+  // the carrier between the outer iterations of the VED filter, which the reference keeps in double (VED.h:64)
+  if (d_in) {
+    rc = stage_input(ctx, MADGPU_PIX_F32, d_in);
+    if (rc) return rc;
+  }
   rc = run_steps(ctx);
   if (rc) return rc;
   rc = stage_output(ctx, MADGPU_PIX_F32, d_out);
@@ -2001,6 +2010,7 @@ int madgpu_solve_device_f32(madgpu_ctx* ctx, const float* d_in, float* d_out, ma
 // ---- cycle-level driving --------------------------------------------------------------------
 static int cycles_begin_common(madgpu_ctx* ctx)
 {
+  ctx->have_result = false;  // cycle-level driving leaves the right-hand side, not the iterate, in f64
   Level& L = ctx->lv[0];
   const size_t bytes64 = (size_t)L.g.plane * L.g.nz * sizeof(double);
   const dim3 b = block3(ctx->dim), g = grid3(L.g, b);

@@ -451,7 +451,9 @@ int madved_run(madved_ctx* ctx, madgpu_ctx* solver, int32_t in_type, const void*
     for (int k = 0; k < 6; ++k) planes[k] = ctx->T[k];
     VCU(cudaStreamSynchronize(ctx->stream));
     if (madgpu_set_tensor_device_f32(solver, planes) != 0) return vfail(ctx, MADGPU_ECUDA, "solver: %s", madgpu_last_error(solver));
-    if (madgpu_solve_device_f32(solver, ctx->image, ctx->image, &sst) != 0) return vfail(ctx, MADGPU_ECUDA, "solver: %s", madgpu_last_error(solver));
+    // the first DiffusionStep starts from the (fp32) input image, the following ones from the solver's own fp64 result; the fp32 copy that
+    // comes back feeds the next Hessian
+    if (madgpu_solve_device_f32(solver, it == 0 ? ctx->image : nullptr, ctx->image, &sst) != 0) return vfail(ctx, MADGPU_ECUDA, "solver: %s", madgpu_last_error(solver));
     ctx->have_hessian = false;  // the image changed
     launches += sst.kernel_launches;
     diffusion_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -189,11 +189,12 @@ class MadSolver:
         self._stats(st)
         return out
 
-    def solve_device(self, d_in: int, d_out: int):
-        """Device-resident dense fp32 image in / out (raw device pointers)."""
+    def solve_device(self, d_in, d_out: int):
+        """Device-resident dense fp32 image in / out (raw device pointers).  d_in = None continues from the fp64 result of the previous
+        solve of this context (the carrier between the VED filter's outer iterations)."""
         st = B.Stats()
         st.struct_size = C.sizeof(B.Stats)
-        self._check(self._lib.madgpu_solve_device_f32(self._ctx, C.c_void_p(int(d_in)), C.c_void_p(int(d_out)), C.byref(st)),
+        self._check(self._lib.madgpu_solve_device_f32(self._ctx, C.c_void_p(int(d_in)) if d_in is not None else None, C.c_void_p(int(d_out)), C.byref(st)),
                     "solve_device")
         return self._stats(st)
 

@@ -349,3 +349,28 @@ def test_fp64_residual_with_fp32_operator_rows(MadSolver, monkeypatch, smoother)
             assert s.last_stats["final_relres"][0] <= 1e-9
     assert cycles["0"] == cycles["1"] and abs(cycles["1"][0] - cyc[0]) <= (0 if smoother == "wj" else 2)
     assert rel_l2(outs["1"], outs["0"]) < 5e-7 and rel_l2(outs["1"], ref) < 1e-6
+
+
+def test_continuing_from_the_fp64_result(MadSolver):
+    """madgpu_solve_device_f32 with d_in == NULL: two time steps in one call == one time step + one continued time step, bit for bit
+    (the fp64 iterate is the carrier, not its fp32 copy); without a previous solve it is a state error."""
+    from multigridanisotropicdiffusion_b200 import MadGpuError
+    shape, sp = (12, 14, 12), (0.3125, 0.3125, 0.5)
+    T, img = random_spd_tensor(shape, seed=4), np.ascontiguousarray(random_image(shape, seed=6), dtype=np.float32)
+    kw = dict(time_step=0.1, smoother=0, iterations_per_grid=2, tolerance=1e-9, max_cycles=40)
+    out2 = np.empty(shape, np.float32)
+    with MadSolver(shape, sp, number_of_steps=2, **kw) as s:
+        s.set_tensor(T)
+        s.solve_device(img.ctypes.data, out2.ctypes.data)  # the emulated device's memory is host memory
+    a, b = np.empty(shape, np.float32), np.empty(shape, np.float32)
+    with MadSolver(shape, sp, number_of_steps=1, **kw) as s:
+        s.set_tensor(T)
+        with pytest.raises(MadGpuError):
+            s.solve_device(None, a.ctypes.data)
+        s.solve_device(img.ctypes.data, a.ctypes.data)
+        s.solve_device(None, b.ctypes.data)
+        # restarting from the fp32 copy instead is a different (rounded) right-hand side
+        c = np.empty(shape, np.float32)
+        s.solve_device(a.ctypes.data, c.ctypes.data)
+    assert np.array_equal(b, out2)
+    assert rel_l2(c, out2) < 1e-6

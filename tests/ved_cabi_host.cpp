@@ -74,10 +74,12 @@ int madgpu_solve_device_f32(madgpu_ctx* c, const float* d_in, float* d_out, madg
 {
   if (!c->tensor_set) { c->err = "tensor not set"; return MADGPU_ESTATE; }
   const size_t nv = (size_t)c->p.size[0] * c->p.size[1] * c->p.size[2];
+  if (d_in) {
+    c->result.resize(nv);
+    for (size_t v = 0; v < nv; ++v) c->result[v] = (double)d_in[v];
+  } else if (c->result.size() != nv) { c->err = "no previous solve to continue from"; return MADGPU_ESTATE; }  // d_in == NULL: the fp64 result of the previous solve
   mo_hier* H = mo_create(3, c->p.size, c->p.spacing, c->p.time_step, c->tensor.data(), c->p.smoother, c->p.omega, c->p.iterations_per_grid, 0);
   if (!H) { c->err = "mo_create failed"; return MADGPU_ECUDA; }
-  c->result.resize(nv);
-  for (size_t v = 0; v < nv; ++v) c->result[v] = (double)d_in[v];
   std::vector<int> cyc(c->p.number_of_steps > 0 ? c->p.number_of_steps : 1);
   const int rc = mo_solve(H, c->p.cycle, c->p.tolerance, c->p.max_cycles, c->p.number_of_steps, c->result.data(), cyc.data(), nullptr, 0);
   mo_destroy(H);
